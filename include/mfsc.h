@@ -1,0 +1,134 @@
+/* mfsc.h -- C ABI of libmfsc_b200.so, the B200 (sm_100a) alignment + coverage library that stands in
+ * for the `nucmer --maxmatch` / `show-coords -r` processes MetaFinisherSC shells out to, and for the
+ * Python per-base coverage loop that consumes their rows.
+ *
+ * Boundary replaced (reference kakitone/MetaFinisherSC, paths relative to its root):
+ *   srcRefactor/repeatPhaserLib/finisherSCCoreLib/alignerRobot.py:46-64   nucmerMummer   -> mfsc_index_build + mfsc_align_batch
+ *   srcRefactor/repeatPhaserLib/finisherSCCoreLib/alignerRobot.py:66-72   showCoorMummer -> mfsc_write_coords
+ *   srcRefactor/repeatPhaserLib/finisherSCCoreLib/alignerRobot.py:7-40    extractMumData -> mfsc_result_rows (rows served from memory)
+ *   srcRefactor/misassemblyFixerLib/adaptorFix.py:21-22                   nucmer default -> params.maxmatch = 0
+ *   srcRefactor/misassemblyFixerLib/merger.py:126-140                     assignCoverage -> mfsc_coverage
+ * The reference has no FFI of its own (it calls os.system); INTEGRATION.md shows the ctypes stub a
+ * maintainer would add.  Plain pointers and sizes only; every function returns 0 on success and a
+ * negative code otherwise, mfsc_last_error() describes the failure.  There is no CPU fallback: without
+ * a CUDA device every entry point that computes returns MFSC_ERR_CUDA.
+ *
+ * Threading: a handle may be used by one thread at a time; distinct handles are independent.
+ */
+#ifndef MFSC_H
+#define MFSC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFSC_OK 0
+#define MFSC_ERR_ARG (-1)
+#define MFSC_ERR_CUDA (-2)
+#define MFSC_ERR_NOMEM (-3)
+#define MFSC_ERR_IO (-4)
+
+/* nucmer options (alignerRobot.py:46-64: defaults, `-b 50` with globalFast, `-l 10` with refinedVersion) */
+typedef struct mfsc_params {
+  int32_t minmatch;    /* -l  20 */
+  int32_t mincluster;  /* -c  65 */
+  int32_t maxgap;      /* -g  90 */
+  int32_t breaklen;    /* -b  200 */
+  int32_t diagdiff;    /* -D  5 */
+  int32_t maxmatch;    /* 1: --maxmatch, 0: default (matches unique in the reference) */
+  int32_t simplify;    /* 1: default, drop shadowed clusters */
+  int32_t band_cap;    /* widest DP band kept, <= 248 */
+  double diagfactor;   /* -d  0.12 */
+  int32_t kmer;        /* index k-mer length, 0 = choose from the reference size */
+  int32_t reserved[3];
+} mfsc_params;
+
+typedef struct mfsc_index mfsc_index;     /* contig index resident in HBM */
+typedef struct mfsc_reads mfsc_reads;     /* read batch resident in HBM */
+typedef struct mfsc_result mfsc_result;   /* rows (and optional intermediate stages) of one batch */
+
+const char* mfsc_last_error(void);
+int mfsc_version(void);
+int mfsc_device_count(int32_t* n);
+int mfsc_set_device(int32_t device);
+void mfsc_default_params(mfsc_params* p);
+
+/* pinned host memory for the buffers handed to the calls below (optional, speeds up the copies) */
+int mfsc_host_alloc(void** p, int64_t bytes);
+int mfsc_host_free(void* p);
+
+/* stage 1.  bases: concatenated record characters (ACGT any case; anything else never matches),
+ * rec_off[n_rec+1]: offsets of the records in bases. */
+int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
+                     mfsc_index** out);
+/* Replication over several GPUs: every rank creates the index with `build_tables` = 0 except the root,
+ * fetches the device buffers and broadcasts them (NCCL via torch.distributed, one call per buffer),
+ * then calls mfsc_index_commit.  info: [0] k, [1] stride, [2] text words, [3] buckets+2, [4] positions,
+ * [5] bytes in HBM, [6] records, [7] bases. */
+int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
+                      int32_t build_tables, int64_t n_positions, mfsc_index** out);
+int mfsc_index_info(const mfsc_index* ix, int64_t info[8]);
+/* ptr/bytes[4]: packed text, invalid mask, bucket heads, positions */
+int mfsc_index_buffers(const mfsc_index* ix, void* ptr[4], int64_t bytes[4]);
+int mfsc_index_build_ms(const mfsc_index* ix, double* ms);
+int mfsc_index_free(mfsc_index* ix);
+
+/* read batch upload (host -> HBM, packs both strands) */
+int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_reads, mfsc_reads** out);
+int mfsc_reads_free(mfsc_reads* r);
+
+#define MFSC_KEEP_MEMS 1       /* keep the sorted maximal exact matches for mfsc_result_mems */
+#define MFSC_KEEP_CLUSTERS 2   /* keep the clusters for mfsc_result_clusters */
+#define MFSC_STOP_SEEDS 4      /* stop after stage 2 */
+#define MFSC_STOP_CLUSTERS 8   /* stop after stage 3 */
+
+/* stages 2-4 on a resident batch */
+int mfsc_align_reads(mfsc_index* ix, mfsc_reads* reads, const mfsc_params* p, int32_t flags, mfsc_result** out);
+/* upload + align + rows back on the host: the call that replaces one nucmer + show-coords job */
+int mfsc_align_batch(mfsc_index* ix, const uint8_t* bases, const int64_t* read_off, int32_t n_reads,
+                     const mfsc_params* p, int32_t flags, mfsc_result** out);
+
+#define MFSC_N_ROWS 0
+#define MFSC_N_MEMS 1
+#define MFSC_N_CLUSTERS 2
+#define MFSC_N_CLUSTER_MATCHES 3
+int64_t mfsc_result_count(const mfsc_result* r, int32_t what);
+/* rows in delta order (read, then contig, then cluster walk); s2/e2 on the forward read, s2 > e2 for
+ * reverse-strand rows; errors/cols give %IDY = 100*(cols-errors)/cols as show-coords computes it */
+int mfsc_result_rows(const mfsc_result* r, int32_t* ref_id, int32_t* qry_id, int32_t* s1, int32_t* e1,
+                     int32_t* s2, int32_t* e2, int32_t* errors, int32_t* cols);
+/* matches sorted by (read, strand, s2, s1): read, strand, s1 (0-based in the separator-joined
+ * reference), s2 (0-based on the strand), len */
+int mfsc_result_mems(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int64_t* s1, int32_t* s2, int32_t* len);
+/* clusters (split at record changes) in emission order: read, strand, record, first match, count;
+ * matches: s1, s2, len as above */
+int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int32_t* rec, int32_t* first,
+                         int32_t* count, int64_t* m_s1, int32_t* m_s2, int32_t* m_len);
+/* stats[16]: 0 DP cells, 1 DP calls, 2 widest band, 3 probes, 4 matches, 5 kernel launches,
+ * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes;
+ * ms[16]: 0 upload+pack, 1 seeds, 2 sort, 3 cluster, 4 extend, 5 compact+download, 6 total */
+int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]);
+int mfsc_result_free(mfsc_result* r);
+
+/* stage 5.  rows selected by the caller (merger.py:171-187): +1 over [s1-1, e1) of contig ref_id.
+ * contig_off[n_contig+1]; cov_out[contig_off[n_contig]]. ms (optional): [0] kernels, [1] total. */
+int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows,
+                  const int64_t* contig_off, int32_t n_contig, int32_t* cov_out, double ms[2]);
+
+/* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
+ * delta file of a row set.  names: NUL-separated, one per record. */
+int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
+                      const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
+                      const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
+                      const char* ref_names, int32_t n_ref, const char* qry_names, int32_t n_qry, int32_t sort_by_ref);
+int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
+                     const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
+                     const int32_t* s2, const int32_t* e2, const int32_t* errors,
+                     const char* ref_names, const int32_t* ref_len, int32_t n_ref,
+                     const char* qry_names, const int32_t* qry_len, int32_t n_qry);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

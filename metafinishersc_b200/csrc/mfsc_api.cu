@@ -1,0 +1,808 @@
+// mfsc_api.cu -- host side of libmfsc_b200.so: HBM residency, stage orchestration on one stream,
+// and the C ABI declared in include/mfsc.h.  See DESIGN.md for the data layout and per-kernel
+// rooflines.  (tests/emu builds this same file with -DMFSC_EMU for CPU-side logic tests.)
+#include "../../include/mfsc.h"
+#include "mfsc_extend.cuh"
+#include "mfsc_coverage.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#ifndef MFSC_EMU
+#include <cub/cub.cuh>
+#endif
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#ifdef MFSC_EMU
+thread_local emu_dim3 emu_threadIdx, emu_blockIdx, emu_blockDim, emu_gridDim;
+#endif
+
+// ------------------------------------------------------------------------------------------
+// device runtime wrappers
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Timer;
+
+#ifdef MFSC_EMU
+struct Dev {
+  cudaStream_t stream = 0;
+  long long launches = 0;
+  bool ok() { return true; }
+  void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+  void free_(void* p) { free(p); }
+  void h2d(void* d, const void* h, size_t n) { if (n) memcpy(d, h, n); }
+  void d2h(void* h, const void* d, size_t n) { if (n) memcpy(h, d, n); }
+  void zero(void* d, size_t n) { if (n) memset(d, 0, n); }
+  void sync() {}
+  int n_sm() { return 4; }
+};
+static bool dev_check(std::string&) { return true; }
+struct Stamp { std::chrono::steady_clock::time_point t; };
+static void stamp(Dev&, Stamp& s) { s.t = std::chrono::steady_clock::now(); }
+static double elapsed_ms(Dev&, Stamp& a, Stamp& b) { return std::chrono::duration<double, std::milli>(b.t - a.t).count(); }
+static void stamp_free(Stamp&) {}
+#else
+static bool g_pool_init = false;
+struct Dev {
+  cudaStream_t stream = 0;
+  long long launches = 0;
+  int sm = 0;
+  bool ok() {
+    if (stream) return true;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return false; }
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    int d = 0; cudaGetDevice(&d);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, d);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return true;
+  }
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes ? bytes : 16, stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  }
+  void free_(void* p) { if (p) cudaFreeAsync(p, stream); }
+  void h2d(void* d, const void* h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream); }
+  void d2h(void* h, const void* d, size_t n) { if (n) { cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); } }
+  void zero(void* d, size_t n) { if (n) cudaMemsetAsync(d, 0, n, stream); }
+  void sync() { cudaStreamSynchronize(stream); }
+  int n_sm() { return sm > 0 ? sm : 148; }
+};
+static bool dev_check(std::string& msg) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { msg = cudaGetErrorString(e); return false; }
+  return true;
+}
+struct Stamp { cudaEvent_t e = nullptr; };
+static void stamp(Dev& D, Stamp& s) { if (!s.e) cudaEventCreate(&s.e); cudaEventRecord(s.e, D.stream); }
+static double elapsed_ms(Dev&, Stamp& a, Stamp& b) { float ms = 0; cudaEventSynchronize(b.e); cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
+static void stamp_free(Stamp& s) { if (s.e) cudaEventDestroy(s.e); s.e = nullptr; }
+#endif
+
+static thread_local Dev g_dev;
+
+template <class T> T* dalloc(Dev& D, size_t n) { return (T*)D.alloc(n * sizeof(T)); }
+
+// grid sizes: a multiple of the SM count (148 on B200)
+static unsigned grid_for(Dev& D, long long work_items, int block, int per_sm) {
+  long long need = (work_items + block - 1) / block;
+  long long cap = (long long)D.n_sm() * per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// stable sort of (key, value) pairs, ascending, on bits [0, end_bit)
+static bool sort_pairs_u32(Dev& D, unsigned* key, unsigned* val, unsigned* key_alt, unsigned* val_alt, long long n, int end_bit,
+                           unsigned** key_out, unsigned** val_out) {
+#ifdef MFSC_EMU
+  (void)end_bit;
+  std::vector<unsigned> idx(n);
+  for (long long i = 0; i < n; i++) idx[i] = (unsigned)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return key[a] < key[b]; });
+  for (long long i = 0; i < n; i++) { key_alt[i] = key[idx[i]]; val_alt[i] = val[idx[i]]; }
+  *key_out = key_alt; *val_out = val_alt;
+  return true;
+#else
+  cub::DoubleBuffer<unsigned> k(key, key_alt), v(val, val_alt);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k, v, (int)n, 0, end_bit, D.stream);
+  void* tmp = D.alloc(tmp_bytes);
+  if (!tmp) return false;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (int)n, 0, end_bit, D.stream);
+  D.free_(tmp);
+  D.launches += 4;
+  *key_out = k.Current(); *val_out = v.Current();
+  return true;
+#endif
+}
+
+static bool sort_pairs_u64(Dev& D, unsigned long long* key, unsigned* val, unsigned long long* key_alt, unsigned* val_alt, long long n,
+                           int end_bit, unsigned** val_out) {
+#ifdef MFSC_EMU
+  (void)end_bit;
+  std::vector<unsigned> idx(n);
+  for (long long i = 0; i < n; i++) idx[i] = (unsigned)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return key[a] < key[b]; });
+  for (long long i = 0; i < n; i++) { key_alt[i] = key[idx[i]]; val_alt[i] = val[idx[i]]; }
+  *val_out = val_alt;
+  return true;
+#else
+  cub::DoubleBuffer<unsigned long long> k(key, key_alt);
+  cub::DoubleBuffer<unsigned> v(val, val_alt);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k, v, (int)n, 0, end_bit, D.stream);
+  void* tmp = D.alloc(tmp_bytes);
+  if (!tmp) return false;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (int)n, 0, end_bit, D.stream);
+  D.free_(tmp);
+  D.launches += 8;
+  *val_out = v.Current();
+  return true;
+#endif
+}
+
+static bool inclusive_sum_u32(Dev& D, unsigned* a, long long n) {
+#ifdef MFSC_EMU
+  unsigned acc = 0;
+  for (long long i = 0; i < n; i++) { acc += a[i]; a[i] = acc; }
+  return true;
+#else
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, a, a, (int)n, D.stream);
+  void* tmp = D.alloc(tmp_bytes);
+  if (!tmp) return false;
+  cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, a, a, (int)n, D.stream);
+  D.free_(tmp);
+  D.launches += 2;
+  return true;
+#endif
+}
+
+static bool exclusive_sum_i32(Dev& D, const int* in, int* out, long long n) {
+#ifdef MFSC_EMU
+  int acc = 0;
+  for (long long i = 0; i < n; i++) { int v = in[i]; out[i] = acc; acc += v; }
+  return true;
+#else
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, D.stream);
+  void* tmp = D.alloc(tmp_bytes);
+  if (!tmp) return false;
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, D.stream);
+  D.free_(tmp);
+  D.launches += 2;
+  return true;
+#endif
+}
+
+static int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
+
+// word layout of a set of sequences (see mfsc_seq.cuh)
+static void layout(const int64_t* off, int n_rec, int both, std::vector<unsigned>& wstart, std::vector<unsigned>& start,
+                   std::vector<int>& len, unsigned& n_words, bool& too_big) {
+  const int n_seq = both ? 2 * n_rec : n_rec;
+  wstart.resize(n_seq + 1); start.resize(n_seq); len.resize(n_seq);
+  unsigned long long w = 1;
+  for (int k = 0; k < n_seq; k++) {
+    int r = both ? (k >> 1) : k;
+    long long l = off[r + 1] - off[r];
+    wstart[k] = (unsigned)w; start[k] = (unsigned)(w * 32); len[k] = (int)l;
+    w += (unsigned long long)(l / 32 + 1);
+  }
+  wstart[n_seq] = (unsigned)w;
+  too_big = (w + 2) * 32ull >= (1ull << 32);
+  n_words = (unsigned)(w + 2);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct SeqDev {
+  unsigned long long* txt = nullptr; unsigned* inv = nullptr; unsigned* start = nullptr; int* len = nullptr;
+  int n_seq = 0; unsigned n_words = 0; long long n_bases = 0;
+  std::vector<unsigned> h_start; std::vector<int> h_len;
+  SeqStore view() const { SeqStore s; s.txt = txt; s.inv = inv; s.start = start; s.len = len; s.n_seq = n_seq; s.n_words = n_words; return s; }
+};
+
+static bool seq_upload(Dev& D, const uint8_t* bases, const int64_t* off, int n_rec, int both, bool pack, SeqDev& S, std::string& err) {
+  std::vector<unsigned> wstart; bool too_big = false;
+  layout(off, n_rec, both, wstart, S.h_start, S.h_len, S.n_words, too_big);
+  if (too_big) { err = "sequence set exceeds 2^32 packed positions"; return false; }
+  S.n_seq = both ? 2 * n_rec : n_rec;
+  S.n_bases = off[n_rec] - off[0];
+  S.txt = dalloc<unsigned long long>(D, S.n_words);
+  S.inv = dalloc<unsigned>(D, S.n_words);
+  S.start = dalloc<unsigned>(D, S.n_seq + 1);
+  S.len = dalloc<int>(D, S.n_seq + 1);
+  if (!S.txt || !S.inv || !S.start || !S.len) { err = "out of device memory (sequence store)"; return false; }
+  D.h2d(S.start, S.h_start.data(), sizeof(unsigned) * S.n_seq);
+  D.h2d(S.len, S.h_len.data(), sizeof(int) * S.n_seq);
+  if (pack) {
+    unsigned char* d_bases = dalloc<unsigned char>(D, (size_t)S.n_bases + 1);
+    long long* d_off = dalloc<long long>(D, n_rec + 1);
+    unsigned* d_wstart = dalloc<unsigned>(D, S.n_seq + 1);
+    if (!d_bases || !d_off || !d_wstart) { err = "out of device memory (upload)"; return false; }
+    std::vector<long long> rel(n_rec + 1);
+    for (int i = 0; i <= n_rec; i++) rel[i] = off[i] - off[0];
+    D.h2d(d_bases, bases + off[0], (size_t)S.n_bases);
+    D.h2d(d_off, rel.data(), sizeof(long long) * (n_rec + 1));
+    D.h2d(d_wstart, wstart.data(), sizeof(unsigned) * (S.n_seq + 1));
+    MFSC_LAUNCH(k_pack, grid_for(D, S.n_words, 256, 16), 256, 0, D.stream, d_bases, d_off, d_wstart, S.n_seq, both, S.n_words, S.txt, S.inv);
+    D.launches++;
+    D.sync();   // host staging vectors go out of scope
+    D.free_(d_bases); D.free_(d_off); D.free_(d_wstart);
+  }
+  return true;
+}
+
+static void seq_free(Dev& D, SeqDev& S) {
+  D.free_(S.txt); D.free_(S.inv); D.free_(S.start); D.free_(S.len);
+  S.txt = nullptr; S.inv = nullptr; S.start = nullptr; S.len = nullptr;
+}
+
+struct mfsc_index {
+  SeqDev ref;
+  unsigned* ostart = nullptr;   // separator-joined coordinate of each record
+  std::vector<unsigned> h_ostart;
+  unsigned* H = nullptr; unsigned* pos = nullptr;
+  int k = 0; long long n_buckets = 0, n_pos = 0;
+  double build_ms = 0;
+};
+
+struct mfsc_reads {
+  SeqDev q;
+  int n_reads = 0;
+  double upload_ms = 0;
+  long long h2d_bytes = 0;
+};
+
+struct mfsc_result {
+  // rows (host)
+  std::vector<int> ref, qry, s1, e1, s2, e2, errs, cols;
+  // mems (host, optional)
+  std::vector<int> m_q, m_strand, m_s2, m_len; std::vector<long long> m_s1;
+  // clusters (host, optional)
+  std::vector<int> c_q, c_strand, c_rec, c_first, c_n, cm_s2, cm_len; std::vector<long long> cm_s1;
+  long long n_mems = 0;
+  int64_t stats[16]; double ms[16];
+};
+
+template <class T, class U> static void copy_out(U* dst, const std::vector<T>& v) { if (dst) for (size_t i = 0; i < v.size(); i++) dst[i] = (U)v[i]; }
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mfsc_last_error(void) { return g_err.c_str(); }
+int mfsc_version(void) { return 100; }
+
+int mfsc_device_count(int32_t* n) {
+#ifdef MFSC_EMU
+  *n = 1; return MFSC_OK;
+#else
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+  *n = c; return MFSC_OK;
+#endif
+}
+
+int mfsc_set_device(int32_t device) {
+#ifdef MFSC_EMU
+  (void)device; return MFSC_OK;
+#else
+  if (g_dev.stream) return fail(MFSC_ERR_ARG, "mfsc_set_device must be called before any other call of the thread");
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(MFSC_ERR_CUDA, "cudaSetDevice failed"); }
+  return MFSC_OK;
+#endif
+}
+
+void mfsc_default_params(mfsc_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->minmatch = 20; p->mincluster = 65; p->maxgap = 90; p->breaklen = 200; p->diagdiff = 5; p->maxmatch = 1; p->simplify = 1;
+  p->band_cap = 248; p->diagfactor = 0.12; p->kmer = 0;
+}
+
+int mfsc_host_alloc(void** p, int64_t bytes) {
+#ifdef MFSC_EMU
+  *p = malloc((size_t)bytes); return *p ? MFSC_OK : MFSC_ERR_NOMEM;
+#else
+  if (!g_dev.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device");
+  if (cudaMallocHost(p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return fail(MFSC_ERR_NOMEM, "cudaMallocHost failed"); }
+  return MFSC_OK;
+#endif
+}
+int mfsc_host_free(void* p) {
+#ifdef MFSC_EMU
+  free(p);
+#else
+  cudaFreeHost(p);
+#endif
+  return MFSC_OK;
+}
+
+static int check_params(const mfsc_params* p) {
+  if (!p) return fail(MFSC_ERR_ARG, "params is NULL");
+  if (p->minmatch < 4 || p->minmatch > 4096) return fail(MFSC_ERR_ARG, "minmatch out of range");
+  if (p->band_cap < 8 || p->band_cap > DP_SLOTS - 8) return fail(MFSC_ERR_ARG, "band_cap must be in [8, 248]");
+  if (p->breaklen < 1 || p->mincluster < 1 || p->maxgap < 0) return fail(MFSC_ERR_ARG, "bad clustering / extension parameter");
+  return MFSC_OK;
+}
+
+static int choose_k(const mfsc_params* p, long long n_bases) {
+  int k = p->kmer;
+  if (k <= 0) {
+    k = 8;
+    while (k < 14 && (1ll << (2 * k)) < 4 * n_bases) k++;   // about a quarter position per bucket or fewer
+  }
+  if (k > p->minmatch) k = p->minmatch;
+  if (k > 15) k = 15;
+  if (k < 4) k = 4;
+  return k;
+}
+
+int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p, int32_t build_tables,
+                      int64_t n_positions, mfsc_index** out) {
+  if (!rec_off || n_rec <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_index_create: bad arguments");
+  if (build_tables && !bases) return fail(MFSC_ERR_ARG, "mfsc_index_create: bases is NULL");
+  int rc = check_params(p); if (rc) return rc;
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  mfsc_index* ix = new mfsc_index();
+  std::string err;
+  Stamp t0, t1;
+  stamp(D, t0);
+  if (!seq_upload(D, bases, rec_off, n_rec, 0, build_tables != 0, ix->ref, err)) { delete ix; return fail(MFSC_ERR_NOMEM, err); }
+  ix->h_ostart.resize(n_rec);
+  for (int r = 0; r < n_rec; r++) ix->h_ostart[r] = (unsigned)(rec_off[r] - rec_off[0] + r);
+  ix->ostart = dalloc<unsigned>(D, n_rec);
+  D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
+  ix->k = choose_k(p, ix->ref.n_bases);
+  ix->n_buckets = 1ll << (2 * ix->k);
+  ix->H = dalloc<unsigned>(D, ix->n_buckets + 2);
+  if (!ix->H || !ix->ostart) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (bucket table)"); }
+  if (build_tables) {
+    D.zero(ix->H, sizeof(unsigned) * (ix->n_buckets + 2));
+    const unsigned g = grid_for(D, ix->ref.n_words, 256, 16);
+    MFSC_LAUNCH(k_index_count, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H);
+    if (!inclusive_sum_u32(D, ix->H, ix->n_buckets + 2)) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
+    unsigned total = 0;
+    D.d2h(&total, ix->H + ix->n_buckets + 1, sizeof(unsigned));
+    ix->n_pos = total;
+    ix->pos = dalloc<unsigned>(D, (size_t)total + 1);
+    if (!ix->pos) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
+    MFSC_LAUNCH(k_index_fill, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H, ix->pos);
+    D.launches += 2;
+  } else {
+    ix->n_pos = n_positions;
+    ix->pos = dalloc<unsigned>(D, (size_t)n_positions + 1);
+    if (!ix->pos) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
+  }
+  stamp(D, t1);
+  D.sync();
+  ix->build_ms = elapsed_ms(D, t0, t1);
+  stamp_free(t0); stamp_free(t1);
+  std::string msg;
+  if (!dev_check(msg)) { return fail(MFSC_ERR_CUDA, "index build: " + msg); }
+  *out = ix;
+  return MFSC_OK;
+}
+
+int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p, mfsc_index** out) {
+  return mfsc_index_create(bases, rec_off, n_rec, p, 1, 0, out);
+}
+
+int mfsc_index_info(const mfsc_index* ix, int64_t info[8]) {
+  if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
+  info[0] = ix->k; info[1] = 0; info[2] = ix->ref.n_words; info[3] = ix->n_buckets + 2; info[4] = ix->n_pos;
+  info[5] = (int64_t)ix->ref.n_words * 12 + (ix->n_buckets + 2) * 4 + (ix->n_pos + 1) * 4;
+  info[6] = ix->ref.n_seq; info[7] = ix->ref.n_bases;
+  return MFSC_OK;
+}
+
+int mfsc_index_buffers(const mfsc_index* ix, void* ptr[4], int64_t bytes[4]) {
+  if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
+  ptr[0] = ix->ref.txt; bytes[0] = (int64_t)ix->ref.n_words * 8;
+  ptr[1] = ix->ref.inv; bytes[1] = (int64_t)ix->ref.n_words * 4;
+  ptr[2] = ix->H; bytes[2] = (ix->n_buckets + 2) * 4;
+  ptr[3] = ix->pos; bytes[3] = (ix->n_pos + 1) * 4;
+  return MFSC_OK;
+}
+
+int mfsc_index_build_ms(const mfsc_index* ix, double* ms) { if (!ix) return fail(MFSC_ERR_ARG, "index is NULL"); *ms = ix->build_ms; return MFSC_OK; }
+
+int mfsc_index_free(mfsc_index* ix) {
+  if (!ix) return MFSC_OK;
+  Dev& D = g_dev;
+  seq_free(D, ix->ref);
+  D.free_(ix->ostart); D.free_(ix->H); D.free_(ix->pos);
+  delete ix;
+  return MFSC_OK;
+}
+
+int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_reads, mfsc_reads** out) {
+  if (!bases || !read_off || n_reads <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_reads_upload: bad arguments");
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  mfsc_reads* r = new mfsc_reads();
+  std::string err;
+  Stamp t0, t1;
+  stamp(D, t0);
+  if (!seq_upload(D, bases, read_off, n_reads, 1, true, r->q, err)) { delete r; return fail(MFSC_ERR_NOMEM, err); }
+  stamp(D, t1);
+  D.sync();
+  r->upload_ms = elapsed_ms(D, t0, t1);
+  stamp_free(t0); stamp_free(t1);
+  r->n_reads = n_reads;
+  r->h2d_bytes = r->q.n_bases + (long long)sizeof(long long) * (n_reads + 1) + 12ll * r->q.n_seq;
+  std::string msg;
+  if (!dev_check(msg)) { return fail(MFSC_ERR_CUDA, "reads upload: " + msg); }
+  *out = r;
+  return MFSC_OK;
+}
+
+int mfsc_reads_free(mfsc_reads* r) {
+  if (!r) return MFSC_OK;
+  seq_free(g_dev, r->q);
+  delete r;
+  return MFSC_OK;
+}
+
+int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32_t flags, mfsc_result** out) {
+  if (!ix || !rd || !out) return fail(MFSC_ERR_ARG, "mfsc_align_reads: bad arguments");
+  int rc = check_params(p); if (rc) return rc;
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  if (ix->k > p->minmatch) return fail(MFSC_ERR_ARG, "index k-mer is longer than minmatch; rebuild the index with these params");
+  const long long launches0 = D.launches;
+  mfsc_result* res = new mfsc_result();
+  memset(res->stats, 0, sizeof(res->stats)); memset(res->ms, 0, sizeof(res->ms));
+  std::vector<void*> garbage;
+  auto keep = [&](void* ptr) { garbage.push_back(ptr); return ptr; };
+  auto cleanup = [&]() { for (void* g : garbage) D.free_(g); garbage.clear(); };
+#define DA(T, name, count) T* name = (T*)keep(D.alloc(sizeof(T) * (size_t)((count) + 1))); if (!name) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (" #name ")"); }
+
+  DevParams P;
+  P.minmatch = p->minmatch; P.mincluster = p->mincluster; P.maxgap = p->maxgap; P.breaklen = p->breaklen; P.diagdiff = p->diagdiff;
+  P.maxmatch = p->maxmatch; P.simplify = p->simplify; P.band_cap = p->band_cap; P.diagfactor = p->diagfactor;
+  P.k = ix->k; P.stride = p->minmatch - ix->k + 1;
+  const SeqStore RS = ix->ref.view(), QS = rd->q.view();
+  const int n_reads = rd->n_reads, n_qs = 2 * n_reads;
+  Stamp ts[8];
+  stamp(D, ts[0]);
+
+  // ---- stage 2: probes -> maximal exact matches ----
+  std::vector<ProbeChunk> chunks;
+  long long n_probes = 0;
+  const int CH = 2048;
+  for (int qs = 0; qs < n_qs; qs++) {
+    int len = rd->q.h_len[qs];
+    int np = len >= P.k ? (len - P.k) / P.stride + 1 : 0;
+    n_probes += np;
+    for (int b = 0; b < np; b += CH) { ProbeChunk c; c.qs = qs; c.pb = b; c.pe = std::min(np, b + CH); chunks.push_back(c); }
+  }
+  DA(ProbeChunk, d_chunks, chunks.size());
+  D.h2d(d_chunks, chunks.data(), sizeof(ProbeChunk) * chunks.size());
+  DA(unsigned, d_counter, 8);
+  long long cap = std::max<long long>(1 << 16, rd->q.n_bases / 16);
+  MemOut mo; unsigned found = 0;
+  int *m_qs = nullptr, *m_s2 = nullptr, *m_len = nullptr, *m_rec = nullptr; unsigned* m_s1 = nullptr;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    m_qs = (int*)D.alloc(sizeof(int) * (cap + 1)); m_s1 = (unsigned*)D.alloc(sizeof(unsigned) * (cap + 1));
+    m_s2 = (int*)D.alloc(sizeof(int) * (cap + 1)); m_len = (int*)D.alloc(sizeof(int) * (cap + 1)); m_rec = (int*)D.alloc(sizeof(int) * (cap + 1));
+    if (!m_qs || !m_s1 || !m_s2 || !m_len || !m_rec) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (matches)"); }
+    D.zero(d_counter, sizeof(unsigned) * 8);
+    mo.qs = m_qs; mo.s1 = m_s1; mo.s2 = m_s2; mo.len = m_len; mo.rec = m_rec; mo.counter = d_counter; mo.capacity = (unsigned)cap;
+    if (!chunks.empty()) {
+      MFSC_LAUNCH(k_seeds, grid_for(D, (long long)chunks.size() * 128, 128, 16), 128, 0, D.stream, RS, ix->ostart, ix->H, ix->pos, QS, d_chunks,
+                  (int)chunks.size(), P, mo);
+      D.launches++;
+    }
+    D.d2h(&found, d_counter, sizeof(unsigned));
+    if ((long long)found <= cap) break;
+    D.free_(m_qs); D.free_(m_s1); D.free_(m_s2); D.free_(m_len); D.free_(m_rec);
+    cap = (long long)found + 1024;
+  }
+  keep(m_qs); keep(m_s1); keep(m_s2); keep(m_len); keep(m_rec);
+  const long long M = found;
+  res->n_mems = M;
+  res->stats[3] = n_probes; res->stats[4] = M;
+  stamp(D, ts[1]);
+
+  // ---- order by (read strand, s2, s1): two stable radix passes over a permutation ----
+  DA(unsigned, perm, M); DA(unsigned, perm_alt, M); DA(unsigned, key1, M); DA(unsigned, key1_alt, M);
+  DA(unsigned long long, key2, M); DA(unsigned long long, key2_alt, M);
+  DA(int, s_qs, M); DA(unsigned, s_s1, M); DA(int, s_s2, M); DA(int, s_len, M); DA(int, s_rec, M);
+  DA(int, seg, n_qs + 1);
+  if (M > 0) {
+    const unsigned g = grid_for(D, M, 256, 16);
+    MFSC_LAUNCH(k_iota, g, 256, 0, D.stream, perm, M);
+    MFSC_LAUNCH(k_sort_key1, g, 256, 0, D.stream, m_s1, M, key1);
+    unsigned *k1o = nullptr, *p1o = nullptr;
+    long long max_pos = (long long)ix->h_ostart.back() + ix->ref.h_len.back() + 1;
+    if (!sort_pairs_u32(D, key1, perm, key1_alt, perm_alt, M, bits_for((unsigned long long)max_pos), &k1o, &p1o)) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (sort)"); }
+    unsigned* p1_other = (p1o == perm) ? perm_alt : perm;
+    MFSC_LAUNCH(k_sort_key, g, 256, 0, D.stream, m_qs, m_s2, p1o, M, key2);
+    unsigned* p2o = nullptr;
+    if (!sort_pairs_u64(D, key2, p1o, key2_alt, p1_other, M, 32 + bits_for((unsigned long long)n_qs), &p2o)) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (sort)"); }
+    MFSC_LAUNCH(k_gather_mems, g, 256, 0, D.stream, p2o, M, m_qs, m_s1, m_s2, m_len, m_rec, s_qs, s_s1, s_s2, s_len, s_rec);
+    D.launches += 4;
+  }
+  MFSC_LAUNCH(k_seg_bounds, grid_for(D, M + 1, 256, 16), 256, 0, D.stream, s_qs, M, n_qs, seg);
+  D.launches++;
+  stamp(D, ts[2]);
+
+  if (flags & MFSC_KEEP_MEMS) {
+    std::vector<unsigned> hs1(M);
+    res->m_q.resize(M); res->m_strand.resize(M); res->m_s2.resize(M); res->m_len.resize(M); res->m_s1.resize(M);
+    D.d2h(res->m_q.data(), s_qs, sizeof(int) * M); D.d2h(hs1.data(), s_s1, sizeof(unsigned) * M);
+    D.d2h(res->m_s2.data(), s_s2, sizeof(int) * M); D.d2h(res->m_len.data(), s_len, sizeof(int) * M);
+    for (long long i = 0; i < M; i++) { res->m_strand[i] = res->m_q[i] & 1; res->m_q[i] >>= 1; res->m_s1[i] = hs1[i]; }
+  }
+
+  long long n_rows = 0;
+  if (!(flags & MFSC_STOP_SEEDS)) {
+    // ---- stage 3: clusters ----
+    ClusterScratch W; ClusterOut O;
+    DA(unsigned, w_s1, M); DA(int, w_s2, M); DA(int, w_len, M); DA(int, w_rec, M); DA(int, w_score, M); DA(int, w_adj, M);
+    DA(int, w_from, M); DA(int, w_uf, M); DA(int, w_ord, M); DA(int, w_tmp, M); DA(unsigned char, w_flag, M);
+    DA(unsigned, o_s1, M); DA(int, o_s2, M); DA(int, o_len, M); DA(int, o_pcf, M); DA(int, o_pcn, M); DA(int, o_pcr, M);
+    DA(int, o_npc, n_qs); DA(int, o_ncm, n_qs);
+    W.s1 = w_s1; W.s2 = w_s2; W.len = w_len; W.rec = w_rec; W.score = w_score; W.adj = w_adj; W.from = w_from; W.uf = w_uf;
+    W.ord = w_ord; W.tmp = w_tmp; W.flag = w_flag;
+    O.s1 = o_s1; O.s2 = o_s2; O.len = o_len; O.pc_first = o_pcf; O.pc_n = o_pcn; O.pc_rec = o_pcr; O.n_pc = o_npc; O.n_cm = o_ncm;
+    MFSC_LAUNCH(k_cluster, grid_for(D, (long long)n_qs * MFSC_LANES, 128, 16), 128, 0, D.stream, s_s1, s_s2, s_len, s_rec, seg, n_qs, P, W, O);
+    D.launches++;
+    stamp(D, ts[3]);
+
+    if (flags & MFSC_KEEP_CLUSTERS) {
+      std::vector<int> hseg(n_qs + 1), hnpc(n_qs), hpcf(M), hpcn(M), hpcr(M), hs2(M), hlen(M);
+      std::vector<unsigned> hs1(M);
+      D.d2h(hseg.data(), seg, sizeof(int) * (n_qs + 1)); D.d2h(hnpc.data(), o_npc, sizeof(int) * n_qs);
+      D.d2h(hpcf.data(), o_pcf, sizeof(int) * M); D.d2h(hpcn.data(), o_pcn, sizeof(int) * M); D.d2h(hpcr.data(), o_pcr, sizeof(int) * M);
+      D.d2h(hs1.data(), o_s1, sizeof(unsigned) * M); D.d2h(hs2.data(), o_s2, sizeof(int) * M); D.d2h(hlen.data(), o_len, sizeof(int) * M);
+      for (int qs = 0; qs < n_qs; qs++)
+        for (int c = 0; c < hnpc[qs]; c++) {
+          int pc = hseg[qs] + c;
+          res->c_q.push_back(qs >> 1); res->c_strand.push_back(qs & 1); res->c_rec.push_back(hpcr[pc]);
+          res->c_first.push_back((int)res->cm_s1.size()); res->c_n.push_back(hpcn[pc]);
+          for (int t = 0; t < hpcn[pc]; t++) { int w = hpcf[pc] + t; res->cm_s1.push_back(hs1[w]); res->cm_s2.push_back(hs2[w]); res->cm_len.push_back(hlen[w]); }
+        }
+    }
+
+    if (!(flags & MFSC_STOP_CLUSTERS)) {
+      // ---- stage 4: extension ----
+      RowsOut R0, R1;
+      DA(int, r_ref, M); DA(int, r_qry, M); DA(int, r_dir, M); DA(int, r_sA, M); DA(int, r_eA, M); DA(int, r_sB, M); DA(int, r_eB, M);
+      DA(int, r_errs, M); DA(int, r_cols, M); DA(int, r_n, n_reads); DA(int, r_off, n_reads + 1);
+      DA(int, x_ord, M); DA(int, x_tmp, M); DA(unsigned char, x_fused, M);
+      DA(unsigned long long, d_stats, 4);
+      D.zero(d_stats, sizeof(unsigned long long) * 4);
+      R0.ref = r_ref; R0.qry = r_qry; R0.dir = r_dir; R0.sA = r_sA; R0.eA = r_eA; R0.sB = r_sB; R0.eB = r_eB; R0.errs = r_errs; R0.cols = r_cols; R0.n_rows = r_n;
+      ExtIn I;
+      I.seg = seg; I.n_pc = o_npc; I.pc_first = o_pcf; I.pc_n = o_pcn; I.pc_rec = o_pcr; I.cm_s1 = o_s1; I.cm_s2 = o_s2; I.cm_len = o_len;
+      I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.fused = x_fused;
+      ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2);
+      const int ext_block = 128;
+      const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
+#ifndef MFSC_EMU
+      cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem);
+#endif
+      MFSC_LAUNCH(k_extend, grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 5), ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st);
+      D.launches++;
+      stamp(D, ts[4]);
+      // ---- compact rows in read order and bring them back ----
+      if (!exclusive_sum_i32(D, r_n, r_off, n_reads + 1)) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
+      int total = 0;
+      D.d2h(&total, r_off + n_reads, sizeof(int));
+      n_rows = total;
+      DA(int, c_ref, n_rows); DA(int, c_qry, n_rows); DA(int, c_dir, n_rows); DA(int, c_sA, n_rows); DA(int, c_eA, n_rows); DA(int, c_sB, n_rows);
+      DA(int, c_eB, n_rows); DA(int, c_errs, n_rows); DA(int, c_cols, n_rows);
+      R1.ref = c_ref; R1.qry = c_qry; R1.dir = c_dir; R1.sA = c_sA; R1.eA = c_eA; R1.sB = c_sB; R1.eB = c_eB; R1.errs = c_errs; R1.cols = c_cols; R1.n_rows = r_n;
+      MFSC_LAUNCH(k_compact_rows, grid_for(D, (long long)n_reads * MFSC_LANES, 128, 16), 128, 0, D.stream, R0, seg, r_off, n_reads, R1);
+      D.launches++;
+      res->ref.resize(n_rows); res->qry.resize(n_rows); res->s1.resize(n_rows); res->e1.resize(n_rows); res->s2.resize(n_rows);
+      res->e2.resize(n_rows); res->errs.resize(n_rows); res->cols.resize(n_rows);
+      D.d2h(res->ref.data(), c_ref, sizeof(int) * n_rows); D.d2h(res->qry.data(), c_qry, sizeof(int) * n_rows);
+      D.d2h(res->s1.data(), c_sA, sizeof(int) * n_rows); D.d2h(res->e1.data(), c_eA, sizeof(int) * n_rows);
+      D.d2h(res->s2.data(), c_sB, sizeof(int) * n_rows); D.d2h(res->e2.data(), c_eB, sizeof(int) * n_rows);
+      D.d2h(res->errs.data(), c_errs, sizeof(int) * n_rows); D.d2h(res->cols.data(), c_cols, sizeof(int) * n_rows);
+      unsigned long long hst[4];
+      D.d2h(hst, d_stats, sizeof(hst));
+      res->stats[0] = (int64_t)hst[0]; res->stats[1] = (int64_t)hst[1]; res->stats[2] = (int64_t)(int)(hst[2] & 0xffffffffull);
+      res->stats[8] = n_rows * 32 + 8;
+      stamp(D, ts[5]);
+    } else { stamp(D, ts[4]); stamp(D, ts[5]); }
+  } else { stamp(D, ts[3]); stamp(D, ts[4]); stamp(D, ts[5]); }
+  D.sync();
+  res->ms[1] = elapsed_ms(D, ts[0], ts[1]); res->ms[2] = elapsed_ms(D, ts[1], ts[2]); res->ms[3] = elapsed_ms(D, ts[2], ts[3]);
+  res->ms[4] = elapsed_ms(D, ts[3], ts[4]); res->ms[5] = elapsed_ms(D, ts[4], ts[5]); res->ms[6] = elapsed_ms(D, ts[0], ts[5]);
+  for (int i = 0; i < 8; i++) stamp_free(ts[i]);
+  res->stats[5] = D.launches - launches0;
+  // algorithmic bytes of the seed kernel: packed query once, one bucket descriptor per probe,
+  // one position per candidate (bounded below by the matches), packed reference under every reported match
+  res->stats[6] = rd->q.n_bases / 2 + 8 * n_probes + 4 * M;
+  cleanup();
+#undef DA
+  std::string msg;
+  if (!dev_check(msg)) { delete res; return fail(MFSC_ERR_CUDA, "align: " + msg); }
+  *out = res;
+  return MFSC_OK;
+}
+
+int mfsc_align_batch(mfsc_index* ix, const uint8_t* bases, const int64_t* read_off, int32_t n_reads, const mfsc_params* p, int32_t flags,
+                     mfsc_result** out) {
+  mfsc_reads* rd = nullptr;
+  int rc = mfsc_reads_upload(bases, read_off, n_reads, &rd);
+  if (rc) return rc;
+  rc = mfsc_align_reads(ix, rd, p, flags, out);
+  if (rc == MFSC_OK) {
+    (*out)->ms[0] = rd->upload_ms; (*out)->ms[6] += rd->upload_ms; (*out)->stats[7] = rd->h2d_bytes;
+    (*out)->stats[5] += 1;
+  }
+  mfsc_reads_free(rd);
+  return rc;
+}
+
+int64_t mfsc_result_count(const mfsc_result* r, int32_t what) {
+  if (!r) return -1;
+  switch (what) {
+    case MFSC_N_ROWS: return (int64_t)r->ref.size();
+    case MFSC_N_MEMS: return (int64_t)r->m_q.size();
+    case MFSC_N_CLUSTERS: return (int64_t)r->c_q.size();
+    case MFSC_N_CLUSTER_MATCHES: return (int64_t)r->cm_s1.size();
+  }
+  return -1;
+}
+
+
+int mfsc_result_rows(const mfsc_result* r, int32_t* ref_id, int32_t* qry_id, int32_t* s1, int32_t* e1, int32_t* s2, int32_t* e2,
+                     int32_t* errors, int32_t* cols) {
+  if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
+  copy_out(ref_id, r->ref); copy_out(qry_id, r->qry); copy_out(s1, r->s1); copy_out(e1, r->e1); copy_out(s2, r->s2); copy_out(e2, r->e2);
+  copy_out(errors, r->errs); copy_out(cols, r->cols);
+  return MFSC_OK;
+}
+
+int mfsc_result_mems(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int64_t* s1, int32_t* s2, int32_t* len) {
+  if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
+  copy_out(qry_id, r->m_q); copy_out(strand, r->m_strand); copy_out(s1, r->m_s1); copy_out(s2, r->m_s2); copy_out(len, r->m_len);
+  return MFSC_OK;
+}
+
+int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int32_t* rec, int32_t* first, int32_t* count, int64_t* m_s1,
+                         int32_t* m_s2, int32_t* m_len) {
+  if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
+  copy_out(qry_id, r->c_q); copy_out(strand, r->c_strand); copy_out(rec, r->c_rec); copy_out(first, r->c_first); copy_out(count, r->c_n);
+  copy_out(m_s1, r->cm_s1); copy_out(m_s2, r->cm_s2); copy_out(m_len, r->cm_len);
+  return MFSC_OK;
+}
+
+int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]) {
+  if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
+  if (stats) memcpy(stats, r->stats, sizeof(r->stats));
+  if (ms) memcpy(ms, r->ms, sizeof(r->ms));
+  return MFSC_OK;
+}
+
+int mfsc_result_free(mfsc_result* r) { delete r; return MFSC_OK; }
+
+int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows, const int64_t* contig_off, int32_t n_contig,
+                  int32_t* cov_out, double ms[2]) {
+  if (n_rows < 0 || !contig_off || n_contig <= 0 || !cov_out) return fail(MFSC_ERR_ARG, "mfsc_coverage: bad arguments");
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  const long long total = contig_off[n_contig];
+  for (int64_t r = 0; r < n_rows; r++) {
+    if (ref_id[r] < 0 || ref_id[r] >= n_contig) return fail(MFSC_ERR_ARG, "mfsc_coverage: contig id out of range");
+    long long len = contig_off[ref_id[r] + 1] - contig_off[ref_id[r]];
+    if (s1[r] < 1 || e1[r] > len || s1[r] > e1[r] + 1) return fail(MFSC_ERR_ARG, "mfsc_coverage: interval outside its contig");
+  }
+  Stamp t0, t1, t2, t3;
+  stamp(D, t0);
+  const long long n_tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+  int* d_ref = dalloc<int>(D, n_rows + 1); int* d_s1 = dalloc<int>(D, n_rows + 1); int* d_e1 = dalloc<int>(D, n_rows + 1);
+  long long* d_off = dalloc<long long>(D, n_contig + 1);
+  int* d_diff = dalloc<int>(D, total + 16); int* d_cov = dalloc<int>(D, total + 16);
+  unsigned long long* d_state = dalloc<unsigned long long>(D, n_tiles + 1);
+  unsigned* d_ticket = dalloc<unsigned>(D, 4);
+  if (!d_ref || !d_s1 || !d_e1 || !d_off || !d_diff || !d_cov || !d_state || !d_ticket) return fail(MFSC_ERR_NOMEM, "out of device memory (coverage)");
+  D.h2d(d_ref, ref_id, sizeof(int) * n_rows); D.h2d(d_s1, s1, sizeof(int) * n_rows); D.h2d(d_e1, e1, sizeof(int) * n_rows);
+  D.h2d(d_off, contig_off, sizeof(long long) * (n_contig + 1));
+  stamp(D, t1);
+  D.zero(d_diff, sizeof(int) * (total + 16)); D.zero(d_state, sizeof(unsigned long long) * (n_tiles + 1)); D.zero(d_ticket, sizeof(unsigned) * 4);
+  if (n_rows > 0) MFSC_LAUNCH(k_cov_diff, grid_for(D, n_rows, 256, 16), 256, 0, D.stream, d_ref, d_s1, d_e1, (long long)n_rows, d_off, total, d_diff);
+  if (total > 0) MFSC_LAUNCH(k_cov_scan, grid_for(D, n_tiles * MFSC_LANES, 256, 8), 256, 0, D.stream, d_diff, total, d_cov, d_state, d_ticket);
+  D.launches += 2;
+  stamp(D, t2);
+  D.d2h(cov_out, d_cov, sizeof(int) * total);
+  stamp(D, t3);
+  D.sync();
+  if (ms) { ms[0] = elapsed_ms(D, t1, t2); ms[1] = elapsed_ms(D, t0, t3); }
+  stamp_free(t0); stamp_free(t1); stamp_free(t2); stamp_free(t3);
+  D.free_(d_ref); D.free_(d_s1); D.free_(d_e1); D.free_(d_off); D.free_(d_diff); D.free_(d_cov); D.free_(d_state); D.free_(d_ticket);
+  std::string msg;
+  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "coverage: " + msg);
+  return MFSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// show-coords / delta text (host)
+// ------------------------------------------------------------------------------------------
+static std::vector<const char*> split_names(const char* blob, int n) {
+  std::vector<const char*> v(n);
+  const char* p = blob;
+  for (int i = 0; i < n; i++) { v[i] = p; p += strlen(p) + 1; }
+  return v;
+}
+
+int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id,
+                      const int32_t* s1, const int32_t* e1, const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
+                      const char* ref_names, int32_t n_ref, const char* qry_names, int32_t n_qry, int32_t sort_by_ref) {
+  if (!path || n_rows < 0) return fail(MFSC_ERR_ARG, "mfsc_write_coords: bad arguments");
+  std::vector<const char*> rn = split_names(ref_names, n_ref), qn = split_names(qry_names, n_qry);
+  std::vector<int64_t> order(n_rows);
+  for (int64_t i = 0; i < n_rows; i++) order[i] = i;
+  if (sort_by_ref) {
+    // show-coords -r: by reference id (string compare), then reference start; ties keep delta order
+    std::vector<int> rank(n_ref);
+    std::vector<int> ids(n_ref);
+    for (int i = 0; i < n_ref; i++) ids[i] = i;
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return strcmp(rn[a], rn[b]) < 0; });
+    for (int i = 0; i < n_ref; i++) rank[ids[i]] = i;
+    for (int i = 1; i < n_ref; i++) if (strcmp(rn[ids[i]], rn[ids[i - 1]]) == 0) rank[ids[i]] = rank[ids[i - 1]];
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (rank[ref_id[a]] != rank[ref_id[b]]) return rank[ref_id[a]] < rank[ref_id[b]];
+      return s1[a] < s1[b];
+    });
+  }
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(MFSC_ERR_IO, std::string("cannot open ") + path);
+  fprintf(f, "%s %s\nNUCMER\n\n    [S1]     [E1]  |     [S2]     [E2]  |  [LEN 1]  [LEN 2]  |  [%% IDY]  | [TAGS]\n", ref_path, qry_path);
+  fprintf(f, "=====================================================================================\n");
+  for (int64_t x = 0; x < n_rows; x++) {
+    int64_t i = order[x];
+    int len1 = abs(e1[i] - s1[i]) + 1, len2 = abs(e2[i] - s2[i]) + 1;
+    float tot = (float)cols[i];
+    float idy = (tot - (float)errors[i]) / tot * 100.0f;
+    fprintf(f, "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s\n", s1[i], e1[i], s2[i], e2[i], len1, len2, (double)idy, rn[ref_id[i]], qn[qry_id[i]]);
+  }
+  fclose(f);
+  return MFSC_OK;
+}
+
+int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id,
+                     const int32_t* s1, const int32_t* e1, const int32_t* s2, const int32_t* e2, const int32_t* errors, const char* ref_names,
+                     const int32_t* ref_len, int32_t n_ref, const char* qry_names, const int32_t* qry_len, int32_t n_qry) {
+  if (!path || n_rows < 0) return fail(MFSC_ERR_ARG, "mfsc_write_delta: bad arguments");
+  std::vector<const char*> rn = split_names(ref_names, n_ref), qn = split_names(qry_names, n_qry);
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(MFSC_ERR_IO, std::string("cannot open ") + path);
+  fprintf(f, "%s %s\nNUCMER\n", ref_path, qry_path);
+  int last_r = -1, last_q = -1;
+  for (int64_t i = 0; i < n_rows; i++) {
+    if (ref_id[i] != last_r || qry_id[i] != last_q) {
+      fprintf(f, ">%s %s %d %d\n", rn[ref_id[i]], qn[qry_id[i]], ref_len[ref_id[i]], qry_len[qry_id[i]]);
+      last_r = ref_id[i]; last_q = qry_id[i];
+    }
+    // header line of one alignment; the indel offset list is not produced by the traceback-free DP
+    fprintf(f, "%d %d %d %d %d %d 0\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i]);
+  }
+  fclose(f);
+  return MFSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// mfsc_cluster.cuh -- stage 3: mgaps-style clustering and chaining of the matches of one query strand
+// (nucmer pipes `mummer | mgaps -l mincluster -s maxgap -d diagdiff -f diagfactor`; reference call
+// site alignerRobot.py:46-64, defaults 65 / 90 / 5 / 0.12).
+//
+// One warp owns the sorted match list of one (read, strand).  Steps, all in the list's own slice
+// of a few scratch arrays in HBM (a strand's list is short and stays in L1/L2):
+//   1. overlap filter on identical diagonals / identical starts      (sequential, lane 0)
+//   2. union-find over pairs closer than maxgap on near diagonals     (sequential, lane 0)
+//   3. components ordered by their smallest member                    (counting sort, lane 0)
+//   4. per component, repeatedly: chain DP whose inner "best predecessor" scan is spread over
+//      the lanes and reduced with shuffles, trace back, emit the chain if it covers at least
+//      mincluster bases, remove it.
+// Emitted chains are split where consecutive matches lie in different reference records.
+#pragma once
+#include "mfsc_seed.cuh"
+
+struct ClusterScratch {
+  // per match (slice = the strand's range in the sorted match arrays)
+  unsigned* s1; int* s2; int* len; int* rec;  // filtered working copy
+  int* score; int* adj; int* from; int* uf; int* ord; int* tmp;
+  unsigned char* flag;                         // bit0 good, bit1 tentative
+};
+
+struct ClusterOut {
+  unsigned* s1; int* s2; int* len;             // cluster matches, written into the strand's slice
+  int* pc_first; int* pc_n; int* pc_rec;       // per split cluster: first match (absolute index), count, record
+  int* n_pc;                                   // [n_qs] split clusters of the strand
+  int* n_cm;                                   // [n_qs] cluster matches of the strand
+};
+
+MFSC_DEV int uf_find(int* uf, int a) {
+  int r = a;
+  while (uf[r] >= 0) r = uf[r];
+  while (uf[a] >= 0) { int nx = uf[a]; uf[a] = r; a = nx; }
+  return r;
+}
+
+MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
+
+MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
+                      int n_qs, DevParams P, ClusterScratch W, ClusterOut O) {
+  const int lane = lane_id();
+  for (long long qs = warp_global(); qs < n_qs; qs += warps_total()) {
+    const int b = seg[qs], e = seg[qs + 1];
+    const int n = e - b;
+    if (n <= 0) {
+      if (lane == 0) { O.n_pc[qs] = 0; O.n_cm[qs] = 0; }
+      continue;
+    }
+    unsigned* s1 = W.s1 + b; int* s2 = W.s2 + b; int* len = W.len + b; int* rec = W.rec + b;
+    int* score = W.score + b; int* adj = W.adj + b; int* from = W.from + b; int* uf = W.uf + b;
+    int* ord = W.ord + b; int* tmp = W.tmp + b;
+    unsigned char* flag = W.flag + b;
+    int N = 0;
+    if (lane == 0) {
+      // ---- 1. filter ----
+      for (int i = 0; i < n; i++) { s1[i] = m_s1[b + i]; s2[i] = m_s2[b + i]; len[i] = m_len[b + i]; rec[i] = m_rec[b + i]; flag[i] = 1; }
+      for (int i = 0; i < n - 1; i++) {
+        if (!(flag[i] & 1)) continue;
+        long long i_diag = (long long)s2[i] - (long long)s1[i];
+        long long i_end = (long long)s2[i] + len[i];
+        for (int j = i + 1; j < n && s2[j] <= i_end; j++) {
+          if (!(flag[j] & 1)) continue;
+          long long j_diag = (long long)s2[j] - (long long)s1[j];
+          if (i_diag == j_diag) {
+            long long j_extent = (long long)len[j] + s2[j] - s2[i];
+            if (j_extent > len[i]) { len[i] = (int)j_extent; i_end = (long long)s2[i] + j_extent; }
+            flag[j] &= (unsigned char)~1;
+          } else if (s1[i] == s1[j] || s2[i] == s2[j]) {
+            long long olap = (s1[i] == s1[j]) ? ((long long)s2[i] + len[i] - s2[j]) : ((long long)s1[i] + len[i] - (long long)s1[j]);
+            if (len[i] < len[j]) {
+              if (olap >= len[i] / 2) { flag[i] &= (unsigned char)~1; break; }
+            } else if (len[j] < len[i]) {
+              if (olap >= len[j] / 2) flag[j] &= (unsigned char)~1;
+            } else {
+              if (olap >= len[i] / 2) {
+                flag[j] |= 2;
+                if (flag[i] & 2) { flag[i] &= (unsigned char)~1; break; }
+              }
+            }
+          }
+        }
+      }
+      for (int i = 0; i < n; i++)
+        if (flag[i] & 1) { s1[N] = s1[i]; s2[N] = s2[i]; len[N] = len[i]; rec[N] = rec[i]; N++; }
+      // ---- 2. union-find ----
+      for (int i = 0; i < N; i++) uf[i] = -1;
+      for (int i = 0; i < N - 1; i++) {
+        long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
+        for (int j = i + 1; j < N; j++) {
+          long long sep = (long long)s2[j] - i_end;
+          if (sep > P.maxgap) break;
+          long long dd = ll_abs(((long long)s2[j] - (long long)s1[j]) - i_diag);
+          long long lim = (long long)(P.diagfactor * (double)sep);
+          if (lim < P.diagdiff) lim = P.diagdiff;
+          if (dd <= lim) {
+            int a = uf_find(uf, i), c = uf_find(uf, j);
+            if (a != c) { if (a < c) uf[c] = a; else uf[a] = c; }
+          }
+        }
+      }
+      // ---- 3. members grouped by component, components by smallest member ----
+      for (int i = 0; i < N; i++) { from[i] = uf_find(uf, i); tmp[i] = 0; }   // from[] = root for now
+      for (int i = 0; i < N; i++) tmp[from[i]]++;
+      int acc = 0;
+      for (int i = 0; i < N; i++) { int c = tmp[i]; tmp[i] = acc; acc += c; }    // tmp[root] = first slot
+      for (int i = 0; i < N; i++) { ord[tmp[from[i]]++] = i; }
+      // after this, component with root r occupies ord[tmp[r]-count .. tmp[r]); score[] keeps the roots
+      for (int i = 0; i < N; i++) score[i] = from[i];
+    }
+    wsync();
+    N = wbcast_i32(N, 0);
+    // ---- 4. chains ----
+    int n_pc = 0, n_cm = 0;  // warp-uniform
+    int c0 = 0;
+    while (c0 < N) {
+      // component = maximal run in ord[] sharing a root (roots are smallest members, runs are ascending)
+      int root = score[ord[c0]];
+      int c1 = c0 + 1;
+      while (c1 < N && score[ord[c1]] == root) c1++;
+      wsync();
+      // members of the component live in ord[c0..c1); work on indices into s1/s2/len
+      int cn = c1 - c0;
+      int* mem = ord + c0;
+      // chain scores reuse score[] of the members: save nothing, roots are no longer needed for them
+      while (cn > 0) {
+        if (cn == 1) {
+          int a = mem[0];
+          if (len[a] >= P.mincluster) {
+            if (lane == 0) {
+              int w = b + n_cm;
+              O.s1[w] = s1[a]; O.s2[w] = s2[a]; O.len[w] = len[a];
+              O.pc_first[b + n_pc] = w; O.pc_n[b + n_pc] = 1; O.pc_rec[b + n_pc] = rec[a];
+            }
+            n_cm++; n_pc++;
+          }
+          cn = 0;
+          break;
+        }
+        // chain DP over the members in list order
+        for (int i = 0; i < cn; i++) {
+          const int a = mem[i];
+          const long long a_s1 = s1[a], a_s2 = s2[a];
+          const int a_len = len[a];
+          long long bestv = (long long)a_len;   // candidates must beat the match alone
+          int bestj = 0x7fffffff, bestadj = 0;
+          for (int j = lane; j < i; j += MFSC_LANES) {
+            const int c = mem[j];
+            long long olap1 = (long long)s1[c] + len[c] - a_s1;
+            long long olap = olap1 > 0 ? olap1 : 0;
+            long long olap2 = (long long)s2[c] + len[c] - a_s2;
+            if (olap2 > olap) olap = olap2;
+            long long pen = olap + ll_abs((a_s2 - a_s1) - ((long long)s2[c] - (long long)s1[c]));
+            long long cand = (long long)score[c] + a_len - pen;
+            if (cand > bestv) { bestv = cand; bestj = j; bestadj = (int)olap; }   // first best within the lane
+          }
+          // first best across lanes: max value, then smallest j
+          long long mv = wmax_i64(bestv);
+          int mj = wmin_i32(bestv == mv ? bestj : 0x7fffffff);
+          if (mj != 0x7fffffff) {
+            int madj = wmax_i32((bestv == mv && bestj == mj) ? bestadj : -0x7fffffff);
+            if (lane == 0) { score[a] = (int)mv; from[a] = mj; adj[a] = madj; }
+          } else {
+            if (lane == 0) { score[a] = a_len; from[a] = -1; adj[a] = 0; }
+          }
+          if (lane == 0) flag[a] = 0;
+          wsync();
+        }
+        // best chain end: first maximum
+        long long key = -1;
+        for (int i = lane; i < cn; i += MFSC_LANES) {
+          long long kk = ((long long)score[mem[i]] << 32) | (unsigned)(0x7fffffff - i);
+          if (kk > key) key = kk;
+        }
+        key = wmax_i64(key);
+        int best = 0x7fffffff - (int)(key & 0xffffffffll);
+        long long total = 0;
+        if (lane == 0) {
+          for (int i = best; i >= 0; i = from[mem[i]]) { flag[mem[i]] = 1; total += len[mem[i]]; }
+        }
+        wsync();
+        total = wbcast_i64(total, 0);
+        if (total >= P.mincluster) {
+          // emit (lane 0), splitting at record changes; overlaps are trimmed off the later match
+          int add_cm = 0, add_pc = 0;
+          if (lane == 0) {
+            bool firstm = true;
+            int lastrec = -1;
+            for (int i = 0; i < cn; i++) {
+              const int a = mem[i];
+              if (!flag[a]) continue;
+              int ad = firstm ? 0 : adj[a];
+              firstm = false;
+              int l = len[a] - ad;
+              if (l <= 0) continue;
+              int w = b + n_cm + add_cm;
+              O.s1[w] = s1[a] + (unsigned)ad; O.s2[w] = s2[a] + ad; O.len[w] = l;
+              if (rec[a] != lastrec) {
+                int pcw = b + n_pc + add_pc;
+                O.pc_first[pcw] = w; O.pc_n[pcw] = 0; O.pc_rec[pcw] = rec[a];
+                add_pc++;
+                lastrec = rec[a];
+              }
+              O.pc_n[b + n_pc + add_pc - 1]++;
+              add_cm++;
+            }
+          }
+          n_cm += wbcast_i32(add_cm, 0);
+          n_pc += wbcast_i32(add_pc, 0);
+        }
+        // remove the chain
+        int w = 0;
+        if (lane == 0) {
+          for (int i = 0; i < cn; i++) if (!flag[mem[i]]) mem[w++] = mem[i];
+        }
+        wsync();
+        cn = wbcast_i32(w, 0);
+      }
+      c0 = c1;
+    }
+    if (lane == 0) { O.n_pc[qs] = n_pc; O.n_cm[qs] = n_cm; }
+  }
+}

@@ -1,0 +1,195 @@
+"""Python handles over the C ABI: contig index, read batches, row sets, coverage.
+
+Thin by design -- numpy buffers in, numpy buffers out; all computation happens in
+libmfsc_b200.so on the GPU (include/mfsc.h).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KEEP_CLUSTERS, KEEP_MEMS, STOP_CLUSTERS, STOP_SEEDS, check, make_params, ptr  # noqa: F401
+
+
+def _as_buf(seqs):
+    """list[bytes] or (uint8 array, int64 offsets) -> (uint8 array, int64 offsets)"""
+    if isinstance(seqs, tuple):
+        buf, off = seqs
+        return np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.int64)
+    return _lib.concat([s.encode() if isinstance(s, str) else bytes(s) for s in seqs])
+
+
+class Rows:
+    """Alignment rows of one batch in delta order, structure of arrays (int32)."""
+    __slots__ = ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols", "stats", "ms", "mems", "clusters")
+
+    def __len__(self):
+        return len(self.s1)
+
+    def idy(self):
+        """%IDY as show-coords computes it: single precision (cols - errors) / cols * 100."""
+        t = self.cols.astype(np.float32)
+        return (t - self.errors.astype(np.float32)) / t * np.float32(100.0)
+
+
+class Index:
+    def __init__(self, L, handle, n_rec):
+        self.L, self.h, self.n_rec = L, handle, n_rec
+
+    def info(self):
+        a = np.zeros(8, dtype=np.int64)
+        check(self.L, self.L.mfsc_index_info(self.h, ptr(a)))
+        return dict(k=int(a[0]), text_words=int(a[2]), buckets=int(a[3]), positions=int(a[4]), hbm_bytes=int(a[5]),
+                    records=int(a[6]), bases=int(a[7]))
+
+    def buffers(self):
+        """[(device pointer, bytes)] x 4: packed text, invalid mask, bucket heads, positions."""
+        p = (ctypes.c_void_p * 4)()
+        b = np.zeros(4, dtype=np.int64)
+        check(self.L, self.L.mfsc_index_buffers(self.h, p, ptr(b)))
+        return [(int(p[i] or 0), int(b[i])) for i in range(4)]
+
+    def build_ms(self):
+        v = ctypes.c_double()
+        check(self.L, self.L.mfsc_index_build_ms(self.h, ctypes.byref(v)))
+        return v.value
+
+    def free(self):
+        if self.h:
+            self.L.mfsc_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Reads:
+    def __init__(self, L, handle, n_reads, n_bases):
+        self.L, self.h, self.n_reads, self.n_bases = L, handle, n_reads, n_bases
+
+    def free(self):
+        if self.h:
+            self.L.mfsc_reads_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, lib=None):
+        self.L = lib if lib is not None else _lib.load()
+
+    def device_count(self):
+        n = ctypes.c_int32()
+        check(self.L, self.L.mfsc_device_count(ctypes.byref(n)))
+        return n.value
+
+    def set_device(self, d):
+        check(self.L, self.L.mfsc_set_device(d))
+
+    # -- stage 1 ---------------------------------------------------------------------------
+    def index(self, contigs, params=None, build_tables=True, n_positions=0):
+        params = params or make_params()
+        buf, off = _as_buf(contigs)
+        h = ctypes.c_void_p()
+        check(self.L, self.L.mfsc_index_create(ptr(buf) if build_tables else None, ptr(off), len(off) - 1,
+                                               ctypes.byref(params), int(build_tables), n_positions, ctypes.byref(h)))
+        return Index(self.L, h, len(off) - 1)
+
+    # -- stages 2-4 ------------------------------------------------------------------------
+    def upload(self, reads):
+        buf, off = _as_buf(reads)
+        h = ctypes.c_void_p()
+        check(self.L, self.L.mfsc_reads_upload(ptr(buf), ptr(off), len(off) - 1, ctypes.byref(h)))
+        return Reads(self.L, h, len(off) - 1, int(off[-1] - off[0]))
+
+    def _collect(self, h, flags):
+        L = self.L
+        try:
+            r = Rows()
+            n = L.mfsc_result_count(h, 0)
+            cols = [np.zeros(n, dtype=np.int32) for _ in range(8)]
+            check(L, L.mfsc_result_rows(h, *[ptr(c) for c in cols]))
+            r.ref_id, r.qry_id, r.s1, r.e1, r.s2, r.e2, r.errors, r.cols = cols
+            st = np.zeros(16, dtype=np.int64)
+            ms = np.zeros(16, dtype=np.float64)
+            check(L, L.mfsc_result_stats(h, ptr(st), ptr(ms)))
+            r.stats = dict(cells=int(st[0]), dp_calls=int(st[1]), max_band=int(st[2]), probes=int(st[3]), mems=int(st[4]),
+                           launches=int(st[5]), seed_bytes=int(st[6]), h2d_bytes=int(st[7]), d2h_bytes=int(st[8]))
+            r.ms = dict(upload=ms[0], seeds=ms[1], sort=ms[2], cluster=ms[3], extend=ms[4], download=ms[5], total=ms[6])
+            r.mems = r.clusters = None
+            if flags & KEEP_MEMS:
+                m = L.mfsc_result_count(h, 1)
+                q, st_, s2, ln = [np.zeros(m, dtype=np.int32) for _ in range(4)]
+                s1 = np.zeros(m, dtype=np.int64)
+                check(L, L.mfsc_result_mems(h, ptr(q), ptr(st_), ptr(s1), ptr(s2), ptr(ln)))
+                r.mems = np.stack([q.astype(np.int64), st_.astype(np.int64), s1, s2.astype(np.int64), ln.astype(np.int64)], axis=1)
+            if flags & KEEP_CLUSTERS:
+                nc, ncm = L.mfsc_result_count(h, 2), L.mfsc_result_count(h, 3)
+                q, st_, rec, first, cnt = [np.zeros(nc, dtype=np.int32) for _ in range(5)]
+                ms1 = np.zeros(ncm, dtype=np.int64)
+                ms2, mln = np.zeros(ncm, dtype=np.int32), np.zeros(ncm, dtype=np.int32)
+                check(L, L.mfsc_result_clusters(h, ptr(q), ptr(st_), ptr(rec), ptr(first), ptr(cnt), ptr(ms1), ptr(ms2), ptr(mln)))
+                r.clusters = (np.stack([q, st_, rec, first, cnt], axis=1).astype(np.int64),
+                              np.stack([ms1, ms2.astype(np.int64), mln.astype(np.int64)], axis=1))
+            return r
+        finally:
+            L.mfsc_result_free(h)
+
+    def align_reads(self, index, reads, params=None, flags=0):
+        """Stages 2-4 on a batch already resident in HBM."""
+        params = params or make_params()
+        h = ctypes.c_void_p()
+        check(self.L, self.L.mfsc_align_reads(index.h, reads.h, ctypes.byref(params), flags, ctypes.byref(h)))
+        return self._collect(h, flags)
+
+    def align(self, index, reads, params=None, flags=0):
+        """Host buffers in, rows out: what one `nucmer` + `show-coords` job produced."""
+        params = params or make_params()
+        buf, off = _as_buf(reads)
+        if len(off) <= 1:
+            r = Rows()
+            z = np.zeros(0, dtype=np.int32)
+            r.ref_id = r.qry_id = r.s1 = r.e1 = r.s2 = r.e2 = r.errors = r.cols = z
+            r.stats, r.ms, r.mems, r.clusters = {}, {}, None, None
+            return r
+        h = ctypes.c_void_p()
+        check(self.L, self.L.mfsc_align_batch(index.h, ptr(buf), ptr(off), len(off) - 1, ctypes.byref(params), flags, ctypes.byref(h)))
+        return self._collect(h, flags)
+
+    # -- stage 5 ---------------------------------------------------------------------------
+    def coverage(self, ref_id, s1, e1, contig_off, want_ms=False):
+        ref_id = np.ascontiguousarray(ref_id, dtype=np.int32)
+        s1 = np.ascontiguousarray(s1, dtype=np.int32)
+        e1 = np.ascontiguousarray(e1, dtype=np.int32)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
+        cov = np.zeros(int(contig_off[-1]), dtype=np.int32)
+        ms = np.zeros(2, dtype=np.float64)
+        check(self.L, self.L.mfsc_coverage(ptr(ref_id), ptr(s1), ptr(e1), len(s1), ptr(contig_off), len(contig_off) - 1,
+                                           ptr(cov), ptr(ms)))
+        return (cov, ms) if want_ms else cov
+
+    # -- text outputs ----------------------------------------------------------------------
+    def write_coords(self, path, rows, ref_names, qry_names, ref_path, qry_path, sort_by_ref=True):
+        rn = b"\0".join(n.encode() for n in ref_names) + b"\0"
+        qn = b"\0".join(n.encode() for n in qry_names) + b"\0"
+        check(self.L, self.L.mfsc_write_coords(path.encode(), ref_path.encode(), qry_path.encode(), len(rows), ptr(rows.ref_id),
+                                               ptr(rows.qry_id), ptr(rows.s1), ptr(rows.e1), ptr(rows.s2), ptr(rows.e2),
+                                               ptr(rows.errors), ptr(rows.cols), rn, len(ref_names), qn, len(qry_names),
+                                               int(sort_by_ref)))
+
+    def write_delta(self, path, rows, ref_names, ref_len, qry_names, qry_len, ref_path, qry_path):
+        rn = b"\0".join(n.encode() for n in ref_names) + b"\0"
+        qn = b"\0".join(n.encode() for n in qry_names) + b"\0"
+        rl = np.ascontiguousarray(ref_len, dtype=np.int32)
+        ql = np.ascontiguousarray(qry_len, dtype=np.int32)
+        check(self.L, self.L.mfsc_write_delta(path.encode(), ref_path.encode(), qry_path.encode(), len(rows), ptr(rows.ref_id),
+                                              ptr(rows.qry_id), ptr(rows.s1), ptr(rows.e1), ptr(rows.s2), ptr(rows.e2),
+                                              ptr(rows.errors), rn, ptr(rl), len(ref_names), qn, ptr(ql), len(qry_names)))

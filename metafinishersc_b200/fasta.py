@@ -1,0 +1,106 @@
+"""FASTA ingest and the read-part splitter of the alignment path.
+
+`split_fasta` restates `fasta-splitter.pl --n-parts N` (reference
+srcRefactor/repeatPhaserLib/fasta-splitter.pl:135-183): greedy split on measure=all byte
+size, records re-wrapped at 60 columns, parts named <base>.part-NN.fasta.  The part
+boundaries define the read batches (and therefore the row order) that
+alignerRobot.largeRvsQAlign (alignerRobot.py:258-297) concatenates.
+"""
+import os
+
+import numpy as np
+
+
+def read_fasta(path):
+    """-> (names list[str], seqs list[bytes]).  Name = header text after '>' (IORobot.py:21)."""
+    names, seqs, cur = [], [], []
+    with open(path, "rb") as f:
+        for line in f:
+            line = line.rstrip(b"\r\n")
+            if not line:
+                continue
+            if line[:1] == b">":
+                if names:
+                    seqs.append(b"".join(cur))
+                names.append(line[1:].decode())
+                cur = []
+            else:
+                cur.append(line)
+    if names:
+        seqs.append(b"".join(cur))
+    return names, seqs
+
+
+def write_fasta(path, names, seqs, line_len=0):
+    with open(path, "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b">" + n.encode() + b"\n")
+            if line_len:
+                for i in range(0, len(s), line_len):
+                    f.write(s[i:i + line_len] + b"\n")
+            else:
+                f.write(s + b"\n")
+
+
+def concat(seqs):
+    """list[bytes] -> (uint8 array of all bases, int64 offsets[n+1])"""
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if seqs:
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    buf = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+def obtain_length(path):
+    """IORobot.obtainLength (IORobot.py:8-30): name -> summed sequence-line length."""
+    names, seqs = read_fasta(path)
+    return {n: len(s) for n, s in zip(names, seqs)}
+
+
+def part_boundaries(names, seqs, n_parts, line_len=60):
+    """Record index ranges [(begin, end), ...] of the parts fasta-splitter.pl would write
+    (fasta-splitter.pl:160-183, measure=all, unix eol)."""
+    def seq_size(name, s):
+        slen = len(s)
+        return slen + len(name) + 1 + (1 + ((slen + line_len - 1) // line_len if line_len else 1))
+    sizes = [seq_size(n, s) for n, s in zip(names, seqs)]
+    total = sum(sizes)
+    parts, begin = [], 0
+    written_total, written_this, part, part_end, opened = 0, 0, 1, int(total / n_parts), False
+    for i, sz in enumerate(sizes):
+        new_total = written_total + sz
+        if (not opened) or (written_this and new_total > part_end and new_total - part_end > part_end - written_total):
+            if opened:
+                parts.append((begin, i))
+                begin = i
+                part += 1
+            opened = True
+            part_end = int(total / n_parts * part) + 1
+            written_this = 0
+        written_this += sz
+        written_total += sz
+    if opened:
+        parts.append((begin, len(sizes)))
+    return parts
+
+
+def split_fasta(path, n_parts, out_dir=None, line_len=60):
+    """Write <base>.part-NN.fasta files; returns their paths.  fasta-splitter.pl writes into
+    the CWD and alignerRobot.py:268-269 then copies them into the folder; callers pass
+    out_dir=folder to land them there directly."""
+    names, seqs = read_fasta(path)
+    base = os.path.basename(path)
+    ext = ""
+    for e in (".fasta", ".faa", ".fna", ".fa"):
+        if base.lower().endswith(e) and len(base) > len(e):
+            base, ext = base[:-len(e)], base[-len(e):]
+            break
+    out_dir = out_dir if out_dir is not None else os.getcwd()
+    num_len = len(str(n_parts))
+    paths = []
+    for p, (b, e) in enumerate(part_boundaries(names, seqs, n_parts, line_len), start=1):
+        stem = base if (".part-" in base and base.rsplit(".part-", 1)[1].isdigit()) else base + ".part"
+        out = os.path.join(out_dir, "%s-%0*d%s" % (stem, num_len, p, ext))
+        write_fasta(out, names[b:e], seqs[b:e], line_len)
+        paths.append(out)
+    return paths
