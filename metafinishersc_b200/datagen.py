@@ -56,7 +56,7 @@ def abun_gap(G=5_000_000, repeat_len=12_000, L=6000, p=0.01, abun=(50, 20), seed
     return dict(reference=[x.tobytes() for x in genomes], contigs=[x.tobytes() for x in contigs], reads=reads)
 
 
-def sc_lr(G=5_000_000, L=10_000, cov=50, p_del=0.075, p_ins=0.075, seed=0, n_reads=None):
+def sc_lr(G=5_000_000, L=10_000, cov=50, p_del=0.075, p_ins=0.075, seed=0, n_reads=None, read_seed=None):
     """BASELINE config 2 (SC_LR_example shape, dataGenerator.py:144-186): one genome with three
     1-kb repeat copies 1 Mbp apart (scaled with G), contig = seg0+seg2+seg1+seg3, reads with
     15% indel error (p_del = p_ins = 0.075)."""
@@ -69,7 +69,7 @@ def sc_lr(G=5_000_000, L=10_000, cov=50, p_del=0.075, p_ins=0.075, seed=0, n_rea
     segs = [genome[:sep], genome[sep:2 * sep], genome[2 * sep:3 * sep], genome[3 * sep:]]
     contig = np.concatenate([segs[0], segs[2], segs[1], segs[3]])
     n = int(G * cov / L) if n_reads is None else n_reads
-    reads, _ = noisy_reads(genome, n, L, p_del, p_ins, np.random.default_rng(2000 + seed))
+    reads, _ = noisy_reads(genome, n, L, p_del, p_ins, np.random.default_rng(2000 + seed if read_seed is None else read_seed))
     return dict(reference=[genome.tobytes()], contigs=[contig.tobytes()], reads=reads)
 
 

@@ -1,0 +1,51 @@
+"""GPU parity: libmfsc_b200.so through the C ABI against the CPU oracle on the same seeded inputs.
+Seeds, clusters, rows (coordinates, errors, columns) and DP cell counts must be bit-exact; %IDY is
+derived from errors/columns so it is exact as well (tolerance 0.01 stated by north_star)."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+CASES = cases.build_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_gpu_matches_oracle(case, gpu_engine, oracle):
+    name, ref, qry, opts = case
+    bad, r, o = cases.run_case(gpu_engine, oracle, ref, qry, opts)
+    assert not bad, "%s: %s" % (name, "; ".join(bad))
+    if len(r):
+        idy = r.idy()
+        want = oracle.idy_of(o["rows"][:, 7], o["rows"][:, 8])
+        assert np.max(np.abs(idy - want)) <= 0.01
+
+
+def test_gpu_coverage(gpu_engine, oracle):
+    rng = np.random.default_rng(0)
+    lens = np.array([5000, 1, 700000, 33, 4096, 1 << 20], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    n = 50000
+    ref = rng.integers(0, len(lens), size=n).astype(np.int32)
+    s1 = (rng.integers(0, 1 << 30, size=n) % lens[ref] + 1).astype(np.int32)
+    e1 = (s1 - 1 + rng.integers(0, 1 << 30, size=n) % (lens[ref] - s1 + 2)).astype(np.int32)
+    e1[::7] = lens[ref][::7]
+    cov = gpu_engine.coverage(ref, s1, e1, off)
+    assert np.array_equal(cov, oracle.coverage(ref, s1, e1, off))
+    assert np.array_equal(gpu_engine.coverage(ref[:0], s1[:0], e1[:0], off), np.zeros(off[-1], dtype=np.int32))
+
+
+def test_gpu_determinism(gpu_engine):
+    from metafinishersc_b200 import engine
+    name, ref, qry, opts = CASES[1]
+    P = engine.make_params(**opts)
+    ix = gpu_engine.index(ref, P)
+    a = gpu_engine.align(ix, qry, P)
+    b = gpu_engine.align(ix, qry, P)
+    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))
+
+
+def test_smoke():
+    import __graft_entry__ as g
+    g.smoke()
