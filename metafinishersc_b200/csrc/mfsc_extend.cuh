@@ -8,7 +8,15 @@
 // cell) whose band is spread over the lanes.  Per cell the DP also carries the number of
 // alignment columns and errors of the path that produced each state, so no traceback matrix is
 // written: the row arithmetic show-coords needs (S1 E1 S2 E2, errors, columns) falls out of the
-// finish cell.  Band state lives in shared memory, 10 KB per warp, updated in place.
+// finish cell.
+//
+// Band state lives in shared memory (9 KB per warp), indexed circularly by the B coordinate j and
+// updated in place.  A cell does not store its three states: it stores what its two gap children
+// will need -- the best "open or extend" value towards (i, j+1) and towards (i+1, j) -- and its
+// best state for the diagonal child, each with the carried (columns, errors) word.  A cell then
+// costs 6 shared loads, 6 shared stores and three 3-way selects.  Slots just outside the band
+// hold a large negative sentinel so no cell tests band membership.  The bases of both sequences
+// are decoded from the 2-bit text into two small circular byte windows 128 positions at a time.
 #pragma once
 #include "mfsc_cluster.cuh"
 
@@ -16,11 +24,14 @@
 #define DP_BAD (-7)
 #define DP_GOPEN (-7)
 #define DP_GCONT (-4)
-#define DP_NEG (-(1 << 29))
+#define DP_NEG (-(1 << 28))     // "unreachable"; never clamped, real scores stay above -2^18
 #define DP_MAX_ALN 10000
-#define DP_SLOTS 256            // circular band storage; band_cap must stay below DP_SLOTS - 2
+#define DP_SLOTS 256            // circular band storage; band_cap must stay below DP_SLOTS - 6
 #define DP_SMASK (DP_SLOTS - 1)
-#define DP_SMEM_INTS (10 * DP_SLOTS)
+#define DP_WIN 512              // decoded-base window per sequence (bytes)
+#define DP_WMASK (DP_WIN - 1)
+#define DP_FILL 128             // bases decoded per refill
+#define DP_SMEM_INTS (8 * DP_SLOTS + 2 * DP_WIN / 4)
 #define AUX_GAP 0x10001         // +1 column, +1 error
 #define AUX_COL 0x10000         // +1 column
 
@@ -31,115 +42,173 @@ struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max
 // View of one sequence: 1-based position i lives at padded position base + i - 1
 struct SeqView { unsigned base; int n; };
 
+struct RowsOut {
+  // alignments of a read are written into the read's slice (first match index of its forward strand)
+  int* ref; int* qry; int* dir; int* sA; int* eA; int* sB; int* eB; int* errs; int* cols;
+  int* n_rows;  // [n_reads]
+};
+
+struct ExtCtx {
+  SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
+  SeqView A; SeqView B[2];
+  RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
+  const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
+  int pc_rc0;                    // split cluster ids >= pc_rc0 belong to the reverse strand
+  const int* pc_first; const int* pc_n; unsigned char* fused;
+  const unsigned* cm_s1; const int* cm_s2; const int* cm_len;
+  unsigned a_ostart;             // separator-joined coordinate of A's first base
+  int ref_id, qry_id, lane;
+};
+
 // Best of three states with the tie rule of the reference DP: D only when strictly above both,
 // I only when strictly above M and not below D.
 MFSC_DEV void best3(int d, int i, int m, int ad, int ai, int am, int& v, int& a) {
-  if (d > i) { if (d > m) { v = d; a = ad; } else { v = m; a = am; } }
-  else if (i > m) { v = i; a = ai; } else { v = m; a = am; }
+  const bool p = d > i;
+  const int x = p ? d : i, ax = p ? ad : ai;
+  const bool q = x > m;
+  v = q ? x : m; a = q ? ax : am;
 }
+
+// decode local positions [from, from + DP_FILL) of a sequence walk (position t -> seq pos s0 + dirn*t, 1-based);
+// the code of position t is stored at window byte t + off
+MFSC_DEV void dp_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_local, int from, int off, unsigned char* win, int lane) {
+  for (int t = from + lane; t < from + DP_FILL; t += MFSC_LANES) {
+    int c = 4;
+    if (t < n_local) c = code_at(S, V.base + (unsigned)(s0 + dirn * t - 1));
+    win[(t + off) & DP_WMASK] = (unsigned char)c;
+  }
+}
+
+MFSC_DEV int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
+MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b; v.z = c; v.w = d; *reinterpret_cast<int4*>(p) = v; }
+
+// one DP cell; Dv/Iv: gap states handed over by the parents, rB/rA: best state of the diagonal parent
+#define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI)                                   \
+  {                                                                                                      \
+    const int j_ = j0 + C;                                                                               \
+    const bool act_ = actg && j_ >= nlo && j_ <= nhi;                                                    \
+    const unsigned ca_ = (aw >> (8 * (3 - C))) & 0xffu, cb_ = (bw >> (8 * C)) & 0xffu;                   \
+    const bool eq_ = ca_ == cb_;                                                                         \
+    const int Mv_ = RB + ((eq_ && ca_ <= 3u) ? DP_GOOD : DP_BAD);                                        \
+    const int xM_ = RA + (eq_ ? AUX_COL : AUX_COL + 1);                                                  \
+    int bv_, ba_, v_, a_;                                                                                \
+    best3(DV, IV, Mv_, XD, XI, xM_, bv_, ba_);                                                           \
+    OB = act_ ? bv_ : DP_NEG; OA = ba_;                                                                  \
+    best3(DV + DP_GCONT, IV + DP_GOPEN, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
+    OD = act_ ? v_ : DP_NEG; OAD = a_ + AUX_GAP;                                                         \
+    best3(DV + DP_GOPEN, IV + DP_GCONT, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
+    OI = act_ ? v_ : DP_NEG; OAI = a_ + AUX_GAP;                                                         \
+    if (act_ && bv_ > lv) { lv = bv_; lj = j_; la = ba_; }                                               \
+  }
 
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
 // A(a0 + dirn*(t-1)), likewise B.  forced: the best cell is re-chosen on every diagonal (the DP
 // never gives up); optimal: reaching the far corner only counts if the best score is there.
-MFSC_DEV DpOut dp_engine(const SeqStore& RS, SeqView Av, int a0, const SeqStore& QS, SeqView Bv, int b0, int dirn,
-                         int N, int M, bool forced, bool optimal, const DevParams& P, int* sm, ExtStats st) {
+// Each lane owns a group of four consecutive j (aligned to 4) per step: 128-bit shared loads and
+// stores, four independent cells of instruction-level parallelism.
+MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N, int M, bool forced, bool optimal) {
+  const SeqStore& RS = E.RS; const SeqStore& QS = E.QS; const SeqView Av = E.A; const SeqView Bv = E.B[dir];
+  const DevParams& P = E.P; const ExtStats st = E.st;
+#ifdef MFSC_EMU
+  int* sm = E.sm;
+#else
+  extern __shared__ int4 dp_smem4[];
+  int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;   // re-derived here so accesses compile to LDS/STS
+#endif
   const int lane = lane_id();
-  int* sD = sm; int* sI = sm + DP_SLOTS; int* sM = sm + 2 * DP_SLOTS;
-  int* aD = sm + 3 * DP_SLOTS; int* aI = sm + 4 * DP_SLOTS; int* aM = sm + 5 * DP_SLOTS;
-  int* bB[2] = {sm + 6 * DP_SLOTS, sm + 7 * DP_SLOTS};
-  int* bA[2] = {sm + 8 * DP_SLOTS, sm + 9 * DP_SLOTS};
+  int* nD = sm; int* naD = sm + DP_SLOTS;            // value / aux handed to cell (i, j+1), stored at j
+  int* nI = sm + 2 * DP_SLOTS; int* naI = sm + 3 * DP_SLOTS;   // handed to cell (i+1, j), stored at j
+  int* bBase = sm + 4 * DP_SLOTS;                    // best state by diagonal parity: value at +0/+DP_SLOTS, aux at +2/+3*DP_SLOTS
+  unsigned char* wA = (unsigned char*)(sm + 8 * DP_SLOTS);
+  unsigned char* wB = wA + DP_WIN;                   // shifted by one: byte j holds the base consumed by column j
+  const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
   const int max_diff = DP_GOOD * P.breaklen;
+  const int band_cap = P.band_cap, breaklen = P.breaklen;
   wsync();
+  // diagonal 0 is the single cell (0,0) with M = 0: its gap children open a gap, its diagonal child reads best = 0
   if (lane == 0) {
-    sD[0] = DP_NEG; sI[0] = DP_NEG; sM[0] = 0; aD[0] = 0; aI[0] = 0; aM[0] = 0;
-    bB[0][0] = 0; bA[0][0] = 0;
+    int* b0p = bBase; int* b1p = bBase + DP_SLOTS;
+    nD[0] = DP_GOPEN; naD[0] = AUX_GAP; nI[0] = DP_GOPEN; naI[0] = AUX_GAP;
+    nD[DP_SMASK] = DP_NEG; nI[1] = DP_NEG;                      // halo of diagonal 0
+    b0p[0] = 0; b0p[2 * DP_SLOTS] = 0; b0p[DP_SMASK] = DP_NEG; b0p[1] = DP_NEG;
+    b1p[DP_SMASK] = DP_NEG; b1p[0] = DP_NEG; b1p[1] = DP_NEG; b1p[2] = DP_NEG;
   }
+  int fillA = 0, fillB = 0;
+  dp_fill(RS, Av, a0, dirn, N, 0, 0, wA, lane); fillA = DP_FILL;
+  dp_fill(QS, Bv, b0, dirn, M, 0, 1, wB, lane); fillB = DP_FILL;
   wsync();
   int high = 0, FinD = 0, FinJ = 0, finAux = 0, lastAux = 0;
-  int p1lo = 0, p1hi = 0, p2lo = 1, p2hi = 0;   // bands of diagonals d-1 and d-2
   int nlo = (1 - N) > 0 ? (1 - N) : 0, nhi = M < 1 ? M : 1;
   unsigned long long cells = 0;
   int maxw = 0;
   int d;
-  for (d = 1; d <= N + M && (d - FinD) <= P.breaklen && nlo <= nhi; d++) {
+  for (d = 1; d <= N + M && (d - FinD) <= breaklen && nlo <= nhi; d++) {
     const int w = nhi - nlo + 1;
     cells += (unsigned long long)w;
     if (w > maxw) maxw = w;
-    int* cB = bB[d & 1]; int* cA = bA[d & 1];     // holds diagonal d-2, receives diagonal d
-    long long lkey = -(1ll << 62); int laux = 0;  // lane-local best of this diagonal (value, then larger j)
-    for (int top = nhi; top >= nlo; top -= MFSC_LANES) {
-      const int j = top - lane;
-      const bool act = j >= nlo;
-      const int i = d - j;
-      int pD = DP_NEG, pI = DP_NEG, pM = DP_NEG, paD = 0, paI = 0, paM = 0;   // parent (i, j-1)
-      int qD = DP_NEG, qI = DP_NEG, qM = DP_NEG, qaD = 0, qaI = 0, qaM = 0;   // parent (i-1, j)
-      int rB = DP_NEG, rA = 0;                                                // parent (i-1, j-1): best state
-      bool hasD = false, hasI = false, hasM = false;
-      if (act) {
-        if (j - 1 >= p1lo && j - 1 <= p1hi) {
-          const int y = (j - 1) & DP_SMASK; hasD = true;
-          pD = sD[y]; pI = sI[y]; pM = sM[y]; paD = aD[y]; paI = aI[y]; paM = aM[y];
-        }
-        if (j >= p1lo && j <= p1hi) {
-          const int y = j & DP_SMASK; hasI = true;
-          qD = sD[y]; qI = sI[y]; qM = sM[y]; qaD = aD[y]; qaI = aI[y]; qaM = aM[y];
-        }
-        if (j - 1 >= p2lo && j - 1 <= p2hi && i >= 1) {
-          const int y = (j - 1) & DP_SMASK; hasM = true;
-          rB = cB[y]; rA = cA[y];
-        }
+    // bases needed on this diagonal: A local index i-1 <= d-nlo-1, B local index j-1 <= nhi-1
+    if (d - nlo > fillA) { dp_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane); fillA += DP_FILL; wsync(); }
+    if (nhi > fillB) { dp_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane); fillB += DP_FILL; wsync(); }
+    int* cB = bBase + (d & 1) * DP_SLOTS; int* cA = cB + 2 * DP_SLOTS;   // holds diagonal d-2, receives diagonal d
+    int lv = -0x7fffffff, lj = -1, la = 0;          // lane-local best of this diagonal (first seen = larger j)
+    const int glo = nlo >> 2;
+    for (int gt = nhi >> 2; gt >= glo; gt -= MFSC_LANES) {
+      const int g = gt - lane;
+      const bool actg = g >= glo;
+      const int j0 = g * 4;
+      int4 vD, vaD, vI, vaI, vB, vA;
+      int sD = DP_NEG, saD = 0, sB = DP_NEG, sA = 0;
+      unsigned aw = 0, bw = 0;
+      vD.x = vD.y = vD.z = vD.w = DP_NEG; vaD = vD; vI = vD; vaI = vD; vB = vD; vA = vD;
+      if (actg) {
+        const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;
+        vD = ld4(nD + y); vaD = ld4(naD + y); vI = ld4(nI + y); vaI = ld4(naI + y); vB = ld4(cB + y); vA = ld4(cA + y);
+        sD = nD[y1]; saD = naD[y1]; sB = cB[y1]; sA = cA[y1];
+        const int as = d - j0 - 4;                    // lowest A window byte of the group (cell 3)
+        const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];
+        aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);
+        bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];
       }
       wsync();
-      if (act) {
-        int Dv = DP_NEG, Iv = DP_NEG, Mv = DP_NEG, xD = 0, xI = 0, xM = 0;
-        if (hasD) {
-          int del = pD > DP_NEG ? pD + DP_GCONT : DP_NEG;
-          int ins = pI > DP_NEG ? pI + DP_GOPEN : DP_NEG;
-          int mat = pM > DP_NEG ? pM + DP_GOPEN : DP_NEG;
-          best3(del, ins, mat, paD, paI, paM, Dv, xD);
-          xD += AUX_GAP;
-          if (Dv <= DP_NEG) Dv = DP_NEG;
-        }
-        if (hasI) {
-          int del = qD > DP_NEG ? qD + DP_GOPEN : DP_NEG;
-          int ins = qI > DP_NEG ? qI + DP_GCONT : DP_NEG;
-          int mat = qM > DP_NEG ? qM + DP_GOPEN : DP_NEG;
-          best3(del, ins, mat, qaD, qaI, qaM, Iv, xI);
-          xI += AUX_GAP;
-          if (Iv <= DP_NEG) Iv = DP_NEG;
-        }
-        if (hasM && rB > DP_NEG) {
-          const int ca = code_at(RS, Av.base + (unsigned)(a0 + dirn * (i - 1) - 1));
-          const int cb = code_at(QS, Bv.base + (unsigned)(b0 + dirn * (j - 1) - 1));
-          Mv = rB + ((ca <= 3 && ca == cb) ? DP_GOOD : DP_BAD);
-          xM = rA + AUX_COL + (ca != cb ? 1 : 0);
-        }
-        const int y = j & DP_SMASK;
-        sD[y] = Dv; sI[y] = Iv; sM[y] = Mv; aD[y] = xD; aI[y] = xI; aM[y] = xM;
-        int bv, ba;
-        best3(Dv, Iv, Mv, xD, xI, xM, bv, ba);
-        cB[y] = bv; cA[y] = ba;
-        const long long key = (long long)bv * 4294967296ll + (long long)j;
-        if (key > lkey) { lkey = key; laux = ba; }
+      if (actg) {
+        int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai;
+        DP_CELL(3, vD.z, vaD.z, vI.w, vaI.w, vB.z, vA.z, o3b, o3a, o3d, o3ad, o3i, o3ai)
+        DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai)
+        DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai)
+        DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai)
+        const int y = j0 & DP_SMASK;
+        st4(cB + y, o0b, o1b, o2b, o3b); st4(cA + y, o0a, o1a, o2a, o3a);
+        st4(nD + y, o0d, o1d, o2d, o3d); st4(naD + y, o0ad, o1ad, o2ad, o3ad);
+        st4(nI + y, o0i, o1i, o2i, o3i); st4(naI + y, o0ai, o1ai, o2ai, o3ai);
       }
       wsync();
     }
+    // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
+    if (lane == 0) {
+      nD[(nlo - 1) & DP_SMASK] = DP_NEG; nI[(nhi + 1) & DP_SMASK] = DP_NEG;
+      cB[(nlo - 1) & DP_SMASK] = DP_NEG; cB[(nhi + 1) & DP_SMASK] = DP_NEG;
+    }
     // diagonal maximum, ties to the larger j
-    const long long dkey = wmax_i64(lkey);
-    const int daux = wmax_i32(lkey == dkey ? laux : -1);
-    const int dmax = (int)((dkey - (dkey & 0xffffffffll)) / 4294967296ll);
-    const int dj = (int)(dkey & 0xffffffffll);
+    const int dmax = wmax_i32(lv);
+    const int dj = wmax_i32(lv == dmax ? lj : -1);
+    const int daux = wmax_i32((lv == dmax && lj == dj) ? la : -1);
     lastAux = daux;
     if (forced || dmax >= high) { high = dmax; FinD = d; FinJ = dj; finAux = daux; }
+    wsync();
     // trim cells that fell more than max_diff below the best (narrows the next diagonal only)
     int lo = 0x7fffffff, hi = -0x7fffffff;
-    for (int j = nlo + lane; j <= nhi; j += MFSC_LANES) {
-      if (high - cB[j & DP_SMASK] <= max_diff) { if (j < lo) lo = j; if (j > hi) hi = j; }
+    const int thr = high - max_diff;
+    for (int g = glo + lane; g <= (nhi >> 2); g += MFSC_LANES) {
+      const int4 v = ld4(cB + ((g * 4) & DP_SMASK));
+      const int j0 = g * 4;
+      if (v.x >= thr && j0 >= nlo && j0 <= nhi) { if (j0 < lo) lo = j0; if (j0 > hi) hi = j0; }
+      if (v.y >= thr && j0 + 1 >= nlo && j0 + 1 <= nhi) { if (j0 + 1 < lo) lo = j0 + 1; if (j0 + 1 > hi) hi = j0 + 1; }
+      if (v.z >= thr && j0 + 2 >= nlo && j0 + 2 <= nhi) { if (j0 + 2 < lo) lo = j0 + 2; if (j0 + 2 > hi) hi = j0 + 2; }
+      if (v.w >= thr && j0 + 3 >= nlo && j0 + 3 <= nhi) { if (j0 + 3 < lo) lo = j0 + 3; if (j0 + 3 > hi) hi = j0 + 3; }
     }
     lo = wmin_i32(lo); hi = wmax_i32(hi);
     if (lo > hi) { lo = nhi + 1; hi = nlo - 1; }
-    while (lo <= hi && hi - lo + 2 > P.band_cap) { if (cB[lo & DP_SMASK] < cB[hi & DP_SMASK]) lo++; else hi--; }
-    p2lo = p1lo; p2hi = p1hi; p1lo = nlo; p1hi = nhi;
+    while (lo <= hi && hi - lo + 2 > band_cap) { if (cB[lo & DP_SMASK] < cB[hi & DP_SMASK]) lo++; else hi--; }
     if (lo > hi) { nlo = 1; nhi = 0; }
     else {
       nlo = lo > d + 1 - N ? lo : d + 1 - N;
@@ -165,24 +234,6 @@ MFSC_DEV DpOut dp_engine(const SeqStore& RS, SeqView Av, int a0, const SeqStore&
 // ------------------------------------------------------------------------------------------
 // cluster walking
 // ------------------------------------------------------------------------------------------
-struct RowsOut {
-  // alignments of a read are written into the read's slice (first match index of its forward strand)
-  int* ref; int* qry; int* dir; int* sA; int* eA; int* sB; int* eB; int* errs; int* cols;
-  int* n_rows;  // [n_reads]
-};
-
-struct ExtCtx {
-  SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
-  SeqView A; SeqView B[2];
-  RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
-  const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
-  int pc_rc0;                    // split cluster ids >= pc_rc0 belong to the reverse strand
-  const int* pc_first; const int* pc_n; unsigned char* fused;
-  const unsigned* cm_s1; const int* cm_s2; const int* cm_len;
-  unsigned a_ostart;             // separator-joined coordinate of A's first base
-  int ref_id, qry_id, lane;
-};
-
 MFSC_DEV int c_dir(const ExtCtx& E, int c) { return E.ord[c] >= E.pc_rc0 ? 1 : 0; }
 MFSC_DEV int c_nm(const ExtCtx& E, int c) { return E.pc_n[E.ord[c]]; }
 MFSC_DEV int c_s1(const ExtCtx& E, int c, int t) { return (int)(E.cm_s1[E.pc_first[E.ord[c]] + t] - E.a_ostart) + 1; }
@@ -194,7 +245,7 @@ MFSC_DEV bool ext_forward(ExtCtx& E, int ci, int tA, int tB, bool forced, bool o
   bool overflow = false;
   if (tA - eA + 1 > DP_MAX_ALN) { tA = eA + DP_MAX_ALN - 1; overflow = true; optimal = true; }
   if (tB - eB + 1 > DP_MAX_ALN) { tB = eB + DP_MAX_ALN - 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine(E.RS, E.A, eA, E.QS, E.B[dir], eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal, E.P, E.sm, E.st);
+  DpOut o = dp_engine(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal);
   // the DP re-aligns the alignment's last column
   wsync();
   if (E.lane == 0) {
@@ -211,7 +262,7 @@ MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
   if (ti >= 0) { tA = E.R.eA[ti]; tB = E.R.eB[ti]; } else { tA = 1; tB = 1; optimal = true; }
   if (sA - tA + 1 > DP_MAX_ALN) { tA = sA - DP_MAX_ALN + 1; overflow = true; optimal = true; }
   if (sB - tB + 1 > DP_MAX_ALN) { tB = sB - DP_MAX_ALN + 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine(E.RS, E.A, sA, E.QS, E.B[dir], sB, -1, sA - tA + 1, sB - tB + 1, false, optimal, E.P, E.sm, E.st);
+  DpOut o = dp_engine(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal);
   bool reached = o.reached;
   if (overflow || ti < 0) reached = false;
   if (reached) {
@@ -225,7 +276,7 @@ MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
     E.al1--;
   } else {
     const int nsA = sA - o.fi + 1, nsB = sB - o.fj + 1;
-    DpOut o2 = dp_engine(E.RS, E.A, nsA, E.QS, E.B[dir], nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false, E.P, E.sm, E.st);
+    DpOut o2 = dp_engine(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false);
     wsync();
     if (E.lane == 0) {
       E.R.cols[ci] += o2.cols - 1; E.R.errs[ci] += o2.errs;
@@ -348,12 +399,12 @@ struct ExtIn {
 static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #endif
 
-MFSC_KERNEL k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st) {
+MFSC_KERNEL_LB(128, 4) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st) {
 #ifdef MFSC_EMU
   int* sm = emu_dp_smem;
 #else
-  extern __shared__ int dp_smem[];
-  int* sm = dp_smem + warp_in_block() * DP_SMEM_INTS;
+  extern __shared__ int4 dp_smem4[];
+  int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;
 #endif
   const int lane = lane_id();
   for (long long q = warp_global(); q < n_reads; q += warps_total()) {

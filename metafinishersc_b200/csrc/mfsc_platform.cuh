@@ -24,8 +24,10 @@
 #define MFSC_LANES 1
 #define MFSC_DEV
 #define MFSC_KERNEL static void
+#define MFSC_KERNEL_LB(T, B) static void
 #define MFSC_HD
 #define MFSC_FORCEINLINE inline
+#define MFSC_NOINLINE static
 struct emu_dim3 { unsigned x, y, z; };
 extern thread_local emu_dim3 emu_threadIdx, emu_blockIdx, emu_blockDim, emu_gridDim;
 #define threadIdx emu_threadIdx
@@ -67,6 +69,7 @@ static inline int dev_ffs64(unsigned long long x) { return x ? __builtin_ctzll(x
 static inline int dev_clz32(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int dev_clz64(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
 static inline int dev_popc32(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned dev_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31u)); }
 static inline unsigned long long dev_brev64(unsigned long long x) {
   unsigned long long r = 0;
   for (int i = 0; i < 64; i++) { r = (r << 1) | (x & 1); x >>= 1; }
@@ -86,8 +89,10 @@ template <class T> static inline T ldg(const T* p) { return *p; }
 #define MFSC_LANES 32
 #define MFSC_DEV __device__ __forceinline__
 #define MFSC_KERNEL __global__ void
+#define MFSC_KERNEL_LB(T, B) __global__ void __launch_bounds__(T, B)
 #define MFSC_HD __host__ __device__
 #define MFSC_FORCEINLINE __forceinline__
+#define MFSC_NOINLINE __device__ __noinline__
 
 #define MFSC_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), stream>>>(__VA_ARGS__)
@@ -119,6 +124,7 @@ MFSC_DEV int dev_ffs64(unsigned long long x) { return __ffsll((long long)x); }
 MFSC_DEV int dev_clz32(unsigned x) { return __clz((int)x); }
 MFSC_DEV int dev_clz64(unsigned long long x) { return __clzll((long long)x); }
 MFSC_DEV int dev_popc32(unsigned x) { return __popc(x); }
+MFSC_DEV unsigned dev_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
 MFSC_DEV unsigned long long dev_brev64(unsigned long long x) { return __brevll(x); }
 MFSC_DEV unsigned ld_volatile_u32(const volatile unsigned* p) { return *p; }
 MFSC_DEV unsigned long long ld_volatile_u64(const volatile unsigned long long* p) { return *p; }
