@@ -24,7 +24,7 @@
 #define DP_BAD (-7)
 #define DP_GOPEN (-7)
 #define DP_GCONT (-4)
-#define DP_NEG (-(1 << 28))     // "unreachable"; never clamped, real scores stay above -2^18
+#define DP_NEG (-(1 << 22))     // "unreachable"; never clamped: real scores stay above -2^18, and (score << 8) must fit an int
 #define DP_MAX_ALN 10000
 #define DP_SLOTS 256            // circular band storage; band_cap must stay below DP_SLOTS - 6
 #define DP_SMASK (DP_SLOTS - 1)
@@ -85,20 +85,16 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
 // one DP cell; Dv/Iv: gap states handed over by the parents, rB/rA: best state of the diagonal parent
 #define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI)                                   \
   {                                                                                                      \
-    const int j_ = j0 + C;                                                                               \
-    const bool act_ = actg && j_ >= nlo && j_ <= nhi;                                                    \
     const unsigned ca_ = (aw >> (8 * (3 - C))) & 0xffu, cb_ = (bw >> (8 * C)) & 0xffu;                   \
     const bool eq_ = ca_ == cb_;                                                                         \
     const int Mv_ = RB + ((eq_ && ca_ <= 3u) ? DP_GOOD : DP_BAD);                                        \
     const int xM_ = RA + (eq_ ? AUX_COL : AUX_COL + 1);                                                  \
-    int bv_, ba_, v_, a_;                                                                                \
-    best3(DV, IV, Mv_, XD, XI, xM_, bv_, ba_);                                                           \
-    OB = act_ ? bv_ : DP_NEG; OA = ba_;                                                                  \
+    int v_, a_;                                                                                          \
+    best3(DV, IV, Mv_, XD, XI, xM_, OB, OA);                                                             \
     best3(DV + DP_GCONT, IV + DP_GOPEN, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
-    OD = act_ ? v_ : DP_NEG; OAD = a_ + AUX_GAP;                                                         \
+    OD = v_; OAD = a_ + AUX_GAP;                                                                         \
     best3(DV + DP_GOPEN, IV + DP_GCONT, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
-    OI = act_ ? v_ : DP_NEG; OAI = a_ + AUX_GAP;                                                         \
-    if (act_ && bv_ > lv) { lv = bv_; lj = j_; la = ba_; }                                               \
+    OI = v_; OAI = a_ + AUX_GAP;                                                                         \
   }
 
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
@@ -150,25 +146,20 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     if (d - nlo > fillA) { dp_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane); fillA += DP_FILL; wsync(); }
     if (nhi > fillB) { dp_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane); fillB += DP_FILL; wsync(); }
     int* cB = bBase + (d & 1) * DP_SLOTS; int* cA = cB + 2 * DP_SLOTS;   // holds diagonal d-2, receives diagonal d
-    int lv = -0x7fffffff, lj = -1, la = 0;          // lane-local best of this diagonal (first seen = larger j)
+    // lane-local best of this diagonal as one key: (score << 8) | (j - nlo); out-of-band cells never enter
+    int lkey = -0x7fffffff;
     const int glo = nlo >> 2;
     for (int gt = nhi >> 2; gt >= glo; gt -= MFSC_LANES) {
-      const int g = gt - lane;
-      const bool actg = g >= glo;
+      const bool actg = gt - lane >= glo;
+      const int g = actg ? gt - lane : glo;          // idle lanes shadow the lowest group (loads only)
       const int j0 = g * 4;
-      int4 vD, vaD, vI, vaI, vB, vA;
-      int sD = DP_NEG, saD = 0, sB = DP_NEG, sA = 0;
-      unsigned aw = 0, bw = 0;
-      vD.x = vD.y = vD.z = vD.w = DP_NEG; vaD = vD; vI = vD; vaI = vD; vB = vD; vA = vD;
-      if (actg) {
-        const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;
-        vD = ld4(nD + y); vaD = ld4(naD + y); vI = ld4(nI + y); vaI = ld4(naI + y); vB = ld4(cB + y); vA = ld4(cA + y);
-        sD = nD[y1]; saD = naD[y1]; sB = cB[y1]; sA = cA[y1];
-        const int as = d - j0 - 4;                    // lowest A window byte of the group (cell 3)
-        const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];
-        aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);
-        bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];
-      }
+      const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;
+      const int4 vD = ld4(nD + y), vaD = ld4(naD + y), vI = ld4(nI + y), vaI = ld4(naI + y), vB = ld4(cB + y), vA = ld4(cA + y);
+      const int sD = nD[y1], saD = naD[y1], sB = cB[y1], sA = cA[y1];
+      const int as = d - j0 - 4;                      // lowest A window byte of the group (cell 3)
+      const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];
+      const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);
+      const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];
       wsync();
       if (actg) {
         int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai;
@@ -176,24 +167,36 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
         DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai)
         DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai)
         DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai)
-        const int y = j0 & DP_SMASK;
+        // cells of the group that lie outside [nlo, nhi] hold junk nobody reads (the halo is rewritten below)
+        // except in the best buffer, which the trim pass and the maximum look at
+        const int r0 = j0 - nlo;
+        if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = DP_NEG;
+        if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = DP_NEG;
+        if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = DP_NEG;
+        if ((unsigned)r0 >= (unsigned)w) o0b = DP_NEG;
         st4(cB + y, o0b, o1b, o2b, o3b); st4(cA + y, o0a, o1a, o2a, o3a);
         st4(nD + y, o0d, o1d, o2d, o3d); st4(naD + y, o0ad, o1ad, o2ad, o3ad);
         st4(nI + y, o0i, o1i, o2i, o3i); st4(naI + y, o0ai, o1ai, o2ai, o3ai);
+        int k = (o3b << 8) + r0 + 3;
+        lkey = k > lkey ? k : lkey;
+        k = (o2b << 8) + r0 + 2; lkey = k > lkey ? k : lkey;
+        k = (o1b << 8) + r0 + 1; lkey = k > lkey ? k : lkey;
+        k = (o0b << 8) + r0; lkey = k > lkey ? k : lkey;
       }
       wsync();
     }
+    // diagonal maximum, ties to the larger j; its carried word is read back from the best buffer
+    const int dkey = wmax_i32(lkey);
+    const int dmax = dkey >> 8;
+    const int dj = nlo + (dkey & 0xff);
+    const int daux = cA[dj & DP_SMASK];
+    lastAux = daux;
+    if (forced || dmax >= high) { high = dmax; FinD = d; FinJ = dj; finAux = daux; }
     // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
     if (lane == 0) {
       nD[(nlo - 1) & DP_SMASK] = DP_NEG; nI[(nhi + 1) & DP_SMASK] = DP_NEG;
       cB[(nlo - 1) & DP_SMASK] = DP_NEG; cB[(nhi + 1) & DP_SMASK] = DP_NEG;
     }
-    // diagonal maximum, ties to the larger j
-    const int dmax = wmax_i32(lv);
-    const int dj = wmax_i32(lv == dmax ? lj : -1);
-    const int daux = wmax_i32((lv == dmax && lj == dj) ? la : -1);
-    lastAux = daux;
-    if (forced || dmax >= high) { high = dmax; FinD = d; FinJ = dj; finAux = daux; }
     wsync();
     // trim cells that fell more than max_diff below the best (narrows the next diagonal only)
     int lo = 0x7fffffff, hi = -0x7fffffff;
@@ -201,10 +204,12 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     for (int g = glo + lane; g <= (nhi >> 2); g += MFSC_LANES) {
       const int4 v = ld4(cB + ((g * 4) & DP_SMASK));
       const int j0 = g * 4;
-      if (v.x >= thr && j0 >= nlo && j0 <= nhi) { if (j0 < lo) lo = j0; if (j0 > hi) hi = j0; }
-      if (v.y >= thr && j0 + 1 >= nlo && j0 + 1 <= nhi) { if (j0 + 1 < lo) lo = j0 + 1; if (j0 + 1 > hi) hi = j0 + 1; }
-      if (v.z >= thr && j0 + 2 >= nlo && j0 + 2 <= nhi) { if (j0 + 2 < lo) lo = j0 + 2; if (j0 + 2 > hi) hi = j0 + 2; }
-      if (v.w >= thr && j0 + 3 >= nlo && j0 + 3 <= nhi) { if (j0 + 3 < lo) lo = j0 + 3; if (j0 + 3 > hi) hi = j0 + 3; }
+      const unsigned m = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
+      if (m) {
+        const int a = j0 + dev_ffs32(m) - 1, z = j0 + 31 - dev_clz32(m);
+        if (a < lo) lo = a;
+        if (z > hi) hi = z;
+      }
     }
     lo = wmin_i32(lo); hi = wmax_i32(hi);
     if (lo > hi) { lo = nhi + 1; hi = nlo - 1; }
