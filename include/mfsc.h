@@ -117,14 +117,17 @@ int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, i
                   const int64_t* contig_off, int32_t n_contig, int32_t* cov_out, double ms[2]);
 
 /* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
- * delta file of a row set.  names: NUL-separated, one per record. */
+ * delta file of a row set.  names: NUL-separated, one per record.  The delta carries the alignment
+ * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors cols`) but no indel offset list: the
+ * traceback-free DP does not produce one, so the 7th header field holds the alignment column count
+ * (MUMmer writes stop codons there, always 0 for nucmer) to keep %IDY reproducible from the file. */
 int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
                       const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
                       const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
                       const char* ref_names, int32_t n_ref, const char* qry_names, int32_t n_qry, int32_t sort_by_ref);
 int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
                      const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
-                     const int32_t* s2, const int32_t* e2, const int32_t* errors,
+                     const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
                      const char* ref_names, const int32_t* ref_len, int32_t n_ref,
                      const char* qry_names, const int32_t* qry_len, int32_t n_qry);
 

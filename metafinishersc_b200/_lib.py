@@ -77,7 +77,7 @@ def bind(path):
     L.mfsc_coverage.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]
     L.mfsc_write_coords.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_i32, ctypes.c_char_p, c_i32, c_i32]
-    L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 7 + \
+    L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_vp, c_i32, ctypes.c_char_p, c_vp, c_i32]
     return L
 

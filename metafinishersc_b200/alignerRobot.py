@@ -1,0 +1,282 @@
+"""Drop-in for the reference's aligner wrapper, same function names and argument meaning
+(reference srcRefactor/repeatPhaserLib/finisherSCCoreLib/alignerRobot.py):
+
+    extractMumData :7     useMummerAlign :42    nucmerMummer :46     showCoorMummer :66
+    combineMultipleCoorMum :74   useMummerAlignBatch :114   transformCoor :242   largeRvsQAlign :258
+
+Where the reference runs `os.system("nucmer ...")` / `os.system("show-coords -r ...")`, these functions
+read the same FASTA paths, run stages 1-4 on the GPU through libmfsc_b200.so and write the same files
+(`<folder><out>.delta`, `<folder><out>Out` or `<folder><specialName>`), so every consumer that opens
+a coords file keeps working.  `mummerLink` is accepted and ignored.  The contig index is cached
+across calls, so the 20 read parts of one reads-vs-contigs alignment share one index instead of
+rebuilding it 20 times.  There is no CPU path: without the CUDA library every aligning call raises.
+"""
+import os
+
+import numpy as np
+
+from . import engine as _engine_mod
+from . import fasta, houseKeeper
+
+_ENGINE = None
+_INDEX_CACHE = {}      # (path, mtime_ns, size, minmatch) -> (Index, names, lens)
+_ROWS_CACHE = {}       # delta path -> RowSet
+_INDEX_CACHE_MAX = 2
+_ROWS_CACHE_MAX = 64
+
+
+def set_engine(E):
+    """Bind the wrapper to an engine (tests bind the host-emulation build; default is the CUDA library)."""
+    global _ENGINE
+    _ENGINE = E
+    clear_caches()
+
+
+def get_engine():
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = _engine_mod.Engine()
+    return _ENGINE
+
+
+def clear_caches():
+    for ix, _, _ in _INDEX_CACHE.values():
+        ix.free()
+    _INDEX_CACHE.clear()
+    _ROWS_CACHE.clear()
+
+
+class RowSet:
+    """Rows of one nucmer job plus what show-coords needs to print them."""
+
+    def __init__(self, rows, ref_names, ref_lens, qry_names, qry_lens, ref_path, qry_path):
+        self.rows, self.ref_names, self.ref_lens = rows, ref_names, ref_lens
+        self.qry_names, self.qry_lens, self.ref_path, self.qry_path = qry_names, qry_lens, ref_path, qry_path
+
+    def order(self):
+        """show-coords -r order: reference id (string compare), then S1; ties keep delta order."""
+        r = self.rows
+        if len(r) == 0:
+            return np.zeros(0, dtype=np.int64)
+        uniq = sorted(set(self.ref_names))
+        rank = {n: i for i, n in enumerate(uniq)}
+        rr = np.array([rank[n] for n in self.ref_names], dtype=np.int64)[r.ref_id]
+        return np.lexsort((np.arange(len(r)), r.s1, rr))
+
+    def datalist(self):
+        """The list extractMumData would parse from the coords text (alignerRobot.py:34)."""
+        r = self.rows
+        o = self.order()
+        idy = r.idy()
+        out = []
+        for i in o:
+            out.append([int(r.s1[i]), int(r.e1[i]), int(r.s2[i]), int(r.e2[i]), abs(int(r.e1[i]) - int(r.s1[i])) + 1,
+                        abs(int(r.e2[i]) - int(r.s2[i])) + 1, float("%.2f" % float(idy[i])), self.ref_names[r.ref_id[i]],
+                        self.qry_names[r.qry_id[i]]])
+        return out
+
+
+def _params(refinedVersion, maxmatch=True):
+    minmatch = 10 if refinedVersion else 20
+    breaklen = 50 if (houseKeeper.globalFast and not refinedVersion) else 200
+    return _engine_mod.make_params(minmatch=minmatch, breaklen=breaklen, maxmatch=maxmatch)
+
+
+def _get_index(E, ref_path, params):
+    st = os.stat(ref_path)
+    key = (os.path.abspath(ref_path), st.st_mtime_ns, st.st_size, params.minmatch)
+    hit = _INDEX_CACHE.get(key)
+    if hit is not None:
+        return hit
+    names, seqs = fasta.read_fasta(ref_path)
+    names = [n.split()[0] if n.split() else n for n in names]      # nucmer ids stop at the first blank
+    while len(_INDEX_CACHE) >= _INDEX_CACHE_MAX:
+        old = next(iter(_INDEX_CACHE))
+        _INDEX_CACHE.pop(old)[0].free()
+    ix = E.index(seqs, params)
+    _INDEX_CACHE[key] = (ix, names, [len(s) for s in seqs])
+    return _INDEX_CACHE[key]
+
+
+def _run_nucmer(prefix, ref_path, qry_path, params):
+    """One nucmer job: rows cached under `<prefix>.delta` and the delta file written."""
+    E = get_engine()
+    delta = prefix + ".delta"
+    if not (os.path.exists(ref_path) and os.path.exists(qry_path)):
+        print("ERROR: Could not find input file(s) %s %s" % (ref_path, qry_path))   # nucmer's failure is ignored upstream too
+        _ROWS_CACHE.pop(delta, None)
+        if os.path.exists(delta):
+            os.remove(delta)
+        return None
+    ix, rnames, rlens = _get_index(E, ref_path, params)
+    qnames, qseqs = fasta.read_fasta(qry_path)
+    qnames = [n.split()[0] if n.split() else n for n in qnames]
+    rows = E.align(ix, qseqs, params)
+    rs = RowSet(rows, rnames, rlens, qnames, [len(s) for s in qseqs], ref_path, qry_path)
+    while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX:
+        _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)))
+    _ROWS_CACHE[delta] = rs
+    E.write_delta(delta, rows, rnames, rlens, qnames, rs.qry_lens, os.path.abspath(ref_path), os.path.abspath(qry_path))
+    return rs
+
+
+def nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion):
+    """alignerRobot.py:46-64: `nucmer [-b 50 | -l 10] --maxmatch -p <folder><out> <folder><ref> <folder|''><qry>`."""
+    qry = queryName if specialForRaw else folderName + queryName
+    return _run_nucmer(folderName + outputName, folderName + referenceName, qry, _params(refinedVersion))
+
+
+def nucmerDefault(mummerLink, prefix, ref_path, qry_path):
+    """The raw default-mode call of adaptorFix.py:21 (`nucmer -p <prefix> <ref> <qry>`, no --maxmatch)."""
+    return _run_nucmer(prefix, ref_path, qry_path, _params(False, maxmatch=False))
+
+
+def _load_delta(delta):
+    """Rows of a delta file this module wrote earlier (resume paths); None when the file is absent."""
+    if not os.path.exists(delta):
+        return None
+    with open(delta) as f:
+        head = f.readline().split()
+        f.readline()
+        rnames, qnames, rlens, qlens, rid, qid = [], [], [], [], {}, {}
+        cols = [[] for _ in range(8)]
+        cur = None
+        for line in f:
+            if line.startswith(">"):
+                a = line[1:].split()
+                if a[0] not in rid:
+                    rid[a[0]] = len(rnames); rnames.append(a[0]); rlens.append(int(a[2]))
+                if a[1] not in qid:
+                    qid[a[1]] = len(qnames); qnames.append(a[1]); qlens.append(int(a[3]))
+                cur = (rid[a[0]], qid[a[1]])
+            else:
+                a = line.split()
+                if len(a) == 7:
+                    for c, v in zip(cols, (cur[0], cur[1], a[0], a[1], a[2], a[3], a[4], a[6])):
+                        c.append(int(v))
+    rows = _engine_mod.Rows()
+    (rows.ref_id, rows.qry_id, rows.s1, rows.e1, rows.s2, rows.e2, rows.errors, rows.cols) = \
+        [np.array(c, dtype=np.int32) for c in cols]
+    rows.stats, rows.ms, rows.mems, rows.clusters = {}, {}, None, None
+    return RowSet(rows, rnames, rlens, qnames, qlens, head[0] if head else "", head[1] if len(head) > 1 else "")
+
+
+def _rowset_for(delta):
+    rs = _ROWS_CACHE.get(delta)
+    return rs if rs is not None else _load_delta(delta)
+
+
+def _write_coords(rs, out_path):
+    if rs is None:
+        open(out_path, "w").close()     # `show-coords missing.delta > out` leaves an empty file
+        return
+    get_engine().write_coords(out_path, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=True)
+
+
+def showCoorMummer(specialForRaw, mummerLink, folderName, outputName, specialName):
+    """alignerRobot.py:66-72: `show-coords -r <folder><out>.delta > <folder><out>Out | <folder><specialName>`."""
+    out = folderName + (specialName if specialForRaw else outputName + "Out")
+    _write_coords(_rowset_for(folderName + outputName + ".delta"), out)
+
+
+def useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw=False, specialName="",
+                   refinedVersion=False):
+    nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion)
+    showCoorMummer(specialForRaw, mummerLink, folderName, outputName, specialName)
+
+
+def zeropadding(i):
+    return "0" + str(i) if i < 10 else str(i)
+
+
+def combineMultipleCoorMum(specialForRaw, mummerLink, folderName, outputName, specialName, numberOfFiles):
+    """alignerRobot.py:74-96: show-coords every part, then `head -5` of part 01 + `tail -n+6` of every part."""
+    print("")
+    for i in range(1, numberOfFiles + 1):
+        showCoorMummer(specialForRaw, mummerLink, folderName, outputName + zeropadding(i), specialName + zeropadding(i))
+    # note: with specialForRaw False showCoorMummer writes <out>NNOut, and the reference then reads <specialName>NN
+    with open(folderName + specialName, "w") as dst:
+        with open(folderName + specialName + "01") as f:
+            dst.writelines(f.readlines()[:5])
+        for i in range(1, numberOfFiles + 1):
+            with open(folderName + specialName + zeropadding(i)) as f:
+                dst.writelines(f.readlines()[5:])
+
+
+def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw=False, refinedVersion=False):
+    """alignerRobot.py:114-236.  workerList: [[outputName, referenceName, queryName, specialName], ...].
+    The Pool / MPI fan-out becomes a loop over the jobs on the GPU (nProc is advisory); jobs that share a
+    reference share its index.  globalLarge reproduces the row order of the 10x10 tiling."""
+    if not houseKeeper.globalLarge:
+        for outputName, referenceName, queryName, specialName in workerList:
+            useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
+        return
+    n_parts = 10
+    for outputName, referenceName, queryName, specialName in workerList:
+        rs = nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion)
+        out = folderName + (specialName if specialForRaw else outputName + "Out")
+        if rs is None:
+            open(out, "w").close()
+            continue
+        # tiles are written reference part by reference part, query part by query part (alignerRobot.py:226-236)
+        rn, rseq = fasta.read_fasta(rs.ref_path)
+        qn, qseq = fasta.read_fasta(rs.qry_path)
+        rpart = np.zeros(len(rn), dtype=np.int64)
+        for p, (b, e) in enumerate(fasta.part_boundaries(rn, rseq, n_parts)):
+            rpart[b:e] = p
+        qpart = np.zeros(len(qn), dtype=np.int64)
+        for p, (b, e) in enumerate(fasta.part_boundaries(qn, qseq, n_parts)):
+            qpart[b:e] = p
+        r = rs.rows
+        base = rs.order()
+        key = np.lexsort((np.arange(len(base)), qpart[r.qry_id[base]], rpart[r.ref_id[base]]))
+        sel = base[key]
+        sub = _engine_mod.Rows()
+        for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            setattr(sub, f, np.ascontiguousarray(getattr(r, f)[sel]))
+        get_engine().write_coords(out, sub, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=False)
+
+
+def transformCoor(dataList):
+    """alignerRobot.py:242-256: order S2/E2 ascending (in place, like the reference)."""
+    newList = []
+    for eachitem in dataList:
+        if not eachitem[2] < eachitem[3]:
+            eachitem[2], eachitem[3] = eachitem[3], eachitem[2]
+        newList.append(eachitem)
+    return newList
+
+
+def extractMumData(folderName, fileName):
+    """alignerRobot.py:7-40: skip 5 lines, then per row [S1, E1, S2, E2, LEN1, LEN2, IDY, refName, qryName]."""
+    dataList = []
+    with open(folderName + fileName, "r") as f:
+        lines = f.readlines()
+    for tmp in lines[5:]:
+        tmp = tmp.rstrip()
+        if len(tmp) == 0:
+            break
+        info = tmp.split("|")
+        first, second, third = info[0].split(), info[1].split(), info[2].split()
+        names = info[-1].split("\t")
+        dataList.append([int(first[0]), int(first[1]), int(second[0]), int(second[1]), int(third[0]), int(third[1]),
+                         float(info[3]), names[0].strip(), names[1].strip()])
+    return dataList
+
+
+def largeRvsQAlign(folderName, numberOfFiles, mummerLink, refFile, qryFile, mumTmpHeader):
+    """alignerRobot.py:258-297: split the query FASTA into parts, align every part against the reference,
+    return the concatenated rows of parts 01..NN (each part in show-coords -r order)."""
+    fasta.split_fasta(folderName + qryFile + ".fasta", numberOfFiles, out_dir=folderName)
+    numberOfFiles = houseKeeper.globalParallelFileNum      # the reference re-reads the global here (alignerRobot.py:271)
+    workerList = []
+    for i in range(1, numberOfFiles + 1):
+        idx = zeropadding(i)
+        workerList.append([mumTmpHeader + idx, refFile + ".fasta", qryFile + ".part-" + idx + ".fasta", mumTmpHeader + idx])
+    useMummerAlignBatch(mummerLink, folderName, workerList, houseKeeper.globalParallel, False)
+    dataList = []
+    for i in range(1, numberOfFiles + 1):
+        rs = _ROWS_CACHE.get(folderName + mumTmpHeader + zeropadding(i) + ".delta")
+        # rows served from memory when this process produced them; identical to parsing the text
+        dataList = dataList + (rs.datalist() if rs is not None else extractMumData(folderName, mumTmpHeader + zeropadding(i) + "Out"))
+    return dataList

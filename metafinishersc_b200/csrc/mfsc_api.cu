@@ -588,13 +588,13 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       RowsOut R0, R1;
       DA(int, r_ref, M); DA(int, r_qry, M); DA(int, r_dir, M); DA(int, r_sA, M); DA(int, r_eA, M); DA(int, r_sB, M); DA(int, r_eB, M);
       DA(int, r_errs, M); DA(int, r_cols, M); DA(int, r_n, n_reads); DA(int, r_off, n_reads + 1);
-      DA(int, x_ord, M); DA(int, x_tmp, M); DA(unsigned char, x_fused, M);
+      DA(int, x_ord, M); DA(int, x_tmp, M); DA(int, x_grp, M); DA(unsigned char, x_fused, M);
       DA(unsigned long long, d_stats, 4);
       D.zero(d_stats, sizeof(unsigned long long) * 4);
       R0.ref = r_ref; R0.qry = r_qry; R0.dir = r_dir; R0.sA = r_sA; R0.eA = r_eA; R0.sB = r_sB; R0.eB = r_eB; R0.errs = r_errs; R0.cols = r_cols; R0.n_rows = r_n;
       ExtIn I;
       I.seg = seg; I.n_pc = o_npc; I.pc_first = o_pcf; I.pc_n = o_pcn; I.pc_rec = o_pcr; I.cm_s1 = o_s1; I.cm_s2 = o_s2; I.cm_len = o_len;
-      I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.fused = x_fused;
+      I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.grp = x_grp; I.fused = x_fused;
       ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2);
       const int ext_block = 128;
       const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
@@ -785,7 +785,7 @@ int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_pa
 }
 
 int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id,
-                     const int32_t* s1, const int32_t* e1, const int32_t* s2, const int32_t* e2, const int32_t* errors, const char* ref_names,
+                     const int32_t* s1, const int32_t* e1, const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols, const char* ref_names,
                      const int32_t* ref_len, int32_t n_ref, const char* qry_names, const int32_t* qry_len, int32_t n_qry) {
   if (!path || n_rows < 0) return fail(MFSC_ERR_ARG, "mfsc_write_delta: bad arguments");
   std::vector<const char*> rn = split_names(ref_names, n_ref), qn = split_names(qry_names, n_qry);
@@ -799,7 +799,7 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
       last_r = ref_id[i]; last_q = qry_id[i];
     }
     // header line of one alignment; the indel offset list is not produced by the traceback-free DP
-    fprintf(f, "%d %d %d %d %d %d 0\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i]);
+    fprintf(f, "%d %d %d %d %d %d %d\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i], cols[i]);
   }
   fclose(f);
   return MFSC_OK;

@@ -397,7 +397,7 @@ struct ExtIn {
   const int* pc_first; const int* pc_n; const int* pc_rec;
   const unsigned* cm_s1; const int* cm_s2; const int* cm_len;
   const unsigned* r_ostart;             // [n_ref]
-  int* ord; int* key_tmp; unsigned char* fused;   // scratch (per-match slices)
+  int* ord; int* key_tmp; int* grp; unsigned char* fused;   // scratch (per-match slices)
 };
 
 #ifdef MFSC_EMU
@@ -420,7 +420,8 @@ MFSC_KERNEL_LB(128, 4) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, 
     int* ord = I.ord + b0;
     int* tmp = I.key_tmp + b0;
     // split cluster ids of the read: forward strand b0..b0+n0, reverse strand b1..b1+n1.
-    // Walking order: record, start in the record, strand, start in the read, emission order.
+    // Walking order: reference records in order of first appearance in that stream (the order of the
+    // delta file's `>ref qry` blocks), then start in the record, strand, start in the read, emission order.
     for (int x = lane; x < nC; x += MFSC_LANES) {
       const int pc = x < n0 ? b0 + x : b1 + (x - n0);
       tmp[x] = pc;
@@ -428,16 +429,23 @@ MFSC_KERNEL_LB(128, 4) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, 
     }
     wsync();
     for (int x = lane; x < nC; x += MFSC_LANES) {
+      const int rec = I.pc_rec[tmp[x]];
+      int f = x;
+      for (int y = 0; y < x; y++) if (I.pc_rec[tmp[y]] == rec) { f = y; break; }
+      I.grp[b0 + x] = f;
+    }
+    wsync();
+    for (int x = lane; x < nC; x += MFSC_LANES) {
       const int pc = tmp[x];
-      const int rec = I.pc_rec[pc]; const unsigned s1 = I.cm_s1[I.pc_first[pc]]; const int dir = pc >= b1 ? 1 : 0;
+      const int grp = I.grp[b0 + x]; const unsigned s1 = I.cm_s1[I.pc_first[pc]]; const int dir = pc >= b1 ? 1 : 0;
       const int s2 = I.cm_s2[I.pc_first[pc]];
       int rank = 0;
       for (int y = 0; y < nC; y++) {
         const int pd = tmp[y];
-        const int rec2 = I.pc_rec[pd]; const unsigned t1 = I.cm_s1[I.pc_first[pd]]; const int dir2 = pd >= b1 ? 1 : 0;
+        const int grp2 = I.grp[b0 + y]; const unsigned t1 = I.cm_s1[I.pc_first[pd]]; const int dir2 = pd >= b1 ? 1 : 0;
         const int t2 = I.cm_s2[I.pc_first[pd]];
         bool before;
-        if (rec2 != rec) before = rec2 < rec;
+        if (grp2 != grp) before = grp2 < grp;
         else if (t1 != s1) before = t1 < s1;
         else if (dir2 != dir) before = dir2 < dir;
         else if (t2 != s2) before = t2 < s2;

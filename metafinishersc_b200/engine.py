@@ -192,4 +192,4 @@ class Engine:
         ql = np.ascontiguousarray(qry_len, dtype=np.int32)
         check(self.L, self.L.mfsc_write_delta(path.encode(), ref_path.encode(), qry_path.encode(), len(rows), ptr(rows.ref_id),
                                               ptr(rows.qry_id), ptr(rows.s1), ptr(rows.e1), ptr(rows.s2), ptr(rows.e2),
-                                              ptr(rows.errors), rn, ptr(rl), len(ref_names), qn, ptr(ql), len(qry_names)))
+                                              ptr(rows.errors), ptr(rows.cols), rn, ptr(rl), len(ref_names), qn, ptr(ql), len(qry_names)))

@@ -606,19 +606,28 @@ void run(const SeqSet& Rf, const SeqSet& Q, const Params& P, int stage_limit, Re
     mgaps(R.mems.data() + m1, (int)(m2 - m1), q, 1, P, R.clusters);
     if (stage_limit < 3) continue;
     // postnuc: split clusters at reference-record boundaries, group per reference record
+    // postnuc: split clusters at reference-record boundaries and group them per reference record; the
+    // groups are walked in order of first appearance in the cluster stream (forward strand first), which
+    // is the order of the `>ref qry` blocks in the delta file (pinned by the reference README.md:111-129,
+    // whose un-sorted show-coords tables list Segkk1/Segkk1 before Segkk0/Segkk1).
     std::vector<std::vector<PCluster> > syn(Rf.n());
+    std::vector<int> rec_order;
     for (size_t c = c0; c < R.clusters.size(); c++) {
       const Cluster& cl = R.clusters[c];
       int lastrec = -1;
       for (size_t t = 0; t < cl.m.size(); t++) {
         int rec = Rf.rec_of(cl.m[t].s1);
-        if (rec != lastrec) { PCluster pc; pc.dir = cl.strand; pc.fused = false; syn[rec].push_back(pc); lastrec = rec; }
+        if (rec != lastrec) {
+          PCluster pc; pc.dir = cl.strand; pc.fused = false;
+          if (syn[rec].empty()) rec_order.push_back(rec);
+          syn[rec].push_back(pc); lastrec = rec;
+        }
         CMatch mm = {cl.m[t].s1 - Rf.start[rec] + 1, cl.m[t].s2 + 1, cl.m[t].len};
         syn[rec].back().m.push_back(mm);
       }
     }
-    for (int rec = 0; rec < Rf.n(); rec++) {
-      if (syn[rec].empty()) continue;
+    for (size_t ro = 0; ro < rec_order.size(); ro++) {
+      int rec = rec_order[ro];
       std::vector<PCluster>& C = syn[rec];
       std::stable_sort(C.begin(), C.end(), [](const PCluster& a, const PCluster& b) {
         if (a.m.front().s1 != b.m.front().s1) return a.m.front().s1 < b.m.front().s1;

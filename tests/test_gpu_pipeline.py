@@ -1,0 +1,76 @@
+"""GPU runs of the host mirror (alignerRobot / IORobot / coverage consumers) and of the full-size
+known answers and properties."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from metafinishersc_b200 import datagen, engine
+from tests import test_golden, test_host_pipeline
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_host_pipeline_gpu(gpu_engine, oracle, tmp_path):
+    test_host_pipeline.run_pipeline(gpu_engine, oracle, tmp_path)
+
+
+def rows_in_delta_order(r, rnames, qnames):
+    idy = r.idy()
+    return [[int(r.s1[i]), int(r.e1[i]), int(r.s2[i]), int(r.e2[i]), abs(int(r.e1[i]) - int(r.s1[i])) + 1,
+             abs(int(r.e2[i]) - int(r.s2[i])) + 1, float("%.2f" % float(idy[i])), rnames[r.ref_id[i]], qnames[r.qry_id[i]]]
+            for i in range(len(r))]
+
+
+def test_gpu_reproduces_readme_tables(gpu_engine):
+    """Reference README.md:111-129 at full 5 Mbp scale: whole-contig exact matches and the delta order."""
+    gold = json.load(open(os.path.join(GOLD, "readme_tables.json")))
+    ref, contigs = test_golden.readme_genomes()
+    names = ["Segkk0", "Segkk1"]
+    P = engine.make_params()
+    ix = gpu_engine.index(ref, P)
+    assert rows_in_delta_order(gpu_engine.align(ix, ref, P), names, names) == gold["reference_vs_reference"]
+    ix.free()
+    ix = gpu_engine.index(contigs, P)
+    assert rows_in_delta_order(gpu_engine.align(ix, ref, P), names, names) == gold["LC_vs_reference"]
+    ix.free()
+
+
+def test_full_size_properties(gpu_engine):
+    """BASELINE cfg2 shape at a size the oracle cannot finish in seconds: size-independent properties."""
+    d = datagen.sc_lr(G=5_000_000, n_reads=3000, seed=100, read_seed=2100)
+    P = engine.make_params()
+    ix = gpu_engine.index(d["contigs"], P)
+    a = gpu_engine.align(ix, d["reads"], P)
+    b = gpu_engine.align(ix, d["reads"], P)
+    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))                    # idempotent / deterministic
+    clen = len(d["contigs"][0])
+    rl = np.array([len(x) for x in d["reads"]])
+    assert len(a) >= 0.9 * len(d["reads"])
+    assert (a.s1 >= 1).all() and (a.e1 <= clen).all() and (a.s1 <= a.e1).all()
+    lo, hi = np.minimum(a.s2, a.e2), np.maximum(a.s2, a.e2)
+    assert (lo >= 1).all() and (hi <= rl[a.qry_id]).all()
+    assert (a.cols >= np.maximum(a.e1 - a.s1, hi - lo) + 1).all() and (a.errors >= 0).all() and (a.errors < a.cols).all()
+    assert (a.s2 < a.e2).all()                                                 # generator emits forward reads only
+    # coverage: checksum of checksums -- the profile sums to the summed interval lengths, and is linear in the rows
+    off = np.array([0, clen], dtype=np.int64)
+    cov = gpu_engine.coverage(a.ref_id, a.s1, a.e1, off)
+    assert int(cov.sum()) == int((a.e1 - a.s1 + 1).sum())
+    h = len(a) // 2
+    c1 = gpu_engine.coverage(a.ref_id[:h], a.s1[:h], a.e1[:h], off)
+    c2 = gpu_engine.coverage(a.ref_id[h:], a.s1[h:], a.e1[h:], off)
+    assert np.array_equal(c1 + c2, cov)
+    # reverse-complemented reads land on the same contig interval with the strand flipped
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    sub = d["reads"][:200]
+    r1 = gpu_engine.align(ix, sub, P)
+    r2 = gpu_engine.align(ix, [x.translate(comp)[::-1] for x in sub], P)
+    k1 = sorted(zip(r1.qry_id.tolist(), r1.s1.tolist(), r1.e1.tolist(), r1.s2.tolist(), r1.e2.tolist(), r1.errors.tolist()))
+    L = np.array([len(x) for x in sub])
+    k2 = sorted(zip(r2.qry_id.tolist(), r2.s1.tolist(), r2.e1.tolist(), (L[r2.qry_id] + 1 - r2.s2).tolist(),
+                    (L[r2.qry_id] + 1 - r2.e2).tolist(), r2.errors.tolist()))
+    assert k1 == k2
+    ix.free()
