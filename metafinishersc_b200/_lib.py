@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmfsc_b200.so")
+LIB_PATH = os.environ.get("MFSC_LIB_DEV") or os.path.join(_HERE, "csrc", "libmfsc_b200.so")   # MFSC_LIB_DEV: developer hook to A/B another build of the same CUDA library
 
 c_i32, c_i64, c_vp, c_dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_double
 

@@ -478,7 +478,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
   DevParams P;
   P.minmatch = p->minmatch; P.mincluster = p->mincluster; P.maxgap = p->maxgap; P.breaklen = p->breaklen; P.diagdiff = p->diagdiff;
   P.maxmatch = p->maxmatch; P.simplify = p->simplify; P.band_cap = p->band_cap; P.diagfactor = p->diagfactor;
-  P.k = ix->k; P.stride = p->minmatch - ix->k + 1;
+  P.k = ix->k; P.stride = p->minmatch - ix->k + 1; P.one = 1;
   const SeqStore RS = ix->ref.view(), QS = rd->q.view();
   const int n_reads = rd->n_reads, n_qs = 2 * n_reads;
   Stamp ts[8];
@@ -601,7 +601,17 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
 #ifndef MFSC_EMU
       cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem);
 #endif
-      MFSC_LAUNCH(k_extend, grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 5), ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st);
+      // persistent grid: as many blocks as are resident at once, reads handed out by ticket
+      unsigned ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 4);
+#ifndef MFSC_EMU
+      {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, ext_block, ext_smem) == cudaSuccess && occ > 0)
+          ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, occ);
+      }
+#endif
+      unsigned* ext_ticket = (unsigned*)(d_stats + 3);
+      MFSC_LAUNCH(k_extend, ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket);
       D.launches++;
       stamp(D, ts[4]);
       // ---- compact rows in read order and bring them back ----

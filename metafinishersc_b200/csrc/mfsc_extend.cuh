@@ -32,8 +32,11 @@
 #define DP_WMASK (DP_WIN - 1)
 #define DP_FILL 128             // bases decoded per refill
 #define DP_SMEM_INTS (8 * DP_SLOTS + 2 * DP_WIN / 4)
-#define AUX_GAP 0x10001         // +1 column, +1 error
-#define AUX_COL 0x10000         // +1 column
+// carried word of a path: (diagonal columns << 16) | mismatching diagonal columns.  Gap columns add nothing;
+// at the finish cell (i, j): columns = i + j - diag, errors = mismatches + i + j - 2*diag.
+#define AUX_PAIR 0x10000
+// integer add issued as a multiply-add with a run-time 1: goes to the FMA pipe instead of the (saturated) ALU pipe
+#define FADD(a, b) ((a) * one + (b))
 
 struct DpOut { int reached, fi, fj, cols, errs; };
 
@@ -83,18 +86,28 @@ MFSC_DEV int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
 MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b; v.z = c; v.w = d; *reinterpret_cast<int4*>(p) = v; }
 
 // one DP cell; Dv/Iv: gap states handed over by the parents, rB/rA: best state of the diagonal parent
+// The three 3-way selections of a cell share their pairwise winners.  Tie rule of the reference DP: the
+// diagonal state wins ties, then the A-gap state, then the B-gap state.
+//   best        : I vs M  -> (vIM,aIM);  D wins iff D > vIM
+//   towards j+1 : D extends (GCONT), I/M open (GOPEN): D wins iff D+GCONT > vIM+GOPEN
+//   towards i+1 : I extends, D/M open: with (vDM,aDM) = D vs M, I wins iff I+GCONT > vDM+GOPEN, or equal when
+//                 vDM came from D (I beats D on ties but loses to M)
 #define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI)                                   \
   {                                                                                                      \
-    const unsigned ca_ = (aw >> (8 * (3 - C))) & 0xffu, cb_ = (bw >> (8 * C)) & 0xffu;                   \
-    const bool eq_ = ca_ == cb_;                                                                         \
-    const int Mv_ = RB + ((eq_ && ca_ <= 3u) ? DP_GOOD : DP_BAD);                                        \
-    const int xM_ = RA + (eq_ ? AUX_COL : AUX_COL + 1);                                                  \
-    int v_, a_;                                                                                          \
-    best3(DV, IV, Mv_, XD, XI, xM_, OB, OA);                                                             \
-    best3(DV + DP_GCONT, IV + DP_GOPEN, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
-    OD = v_; OAD = a_ + AUX_GAP;                                                                         \
-    best3(DV + DP_GOPEN, IV + DP_GCONT, Mv_ + DP_GOPEN, XD, XI, xM_, v_, a_);                            \
-    OI = v_; OAI = a_ + AUX_GAP;                                                                         \
+    const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;             \
+    const int Mv_ = FADD(RB, nm_ ? DP_BAD : DP_GOOD);                                                    \
+    const int xM_ = RA + (ne_ ? AUX_PAIR + 1 : AUX_PAIR);                                                \
+    const bool p1_ = IV > Mv_, p2_ = DV > Mv_;                                                           \
+    const int vIM_ = p1_ ? IV : Mv_, aIM_ = p1_ ? XI : xM_;                                              \
+    const int vDM_ = p2_ ? DV : Mv_, aDM_ = p2_ ? XD : xM_;                                              \
+    const bool pb_ = DV > vIM_;                                                                          \
+    OB = pb_ ? DV : vIM_; OA = pb_ ? XD : aIM_;                                                          \
+    const int e_ = FADD(DV, DP_GCONT), c_ = FADD(vIM_, DP_GOPEN);                                        \
+    const bool pd_ = e_ > c_;                                                                            \
+    OD = pd_ ? e_ : c_; OAD = pd_ ? XD : aIM_;                                                           \
+    const int f_ = FADD(IV, DP_GCONT), c2_ = FADD(vDM_, DP_GOPEN);                                       \
+    const bool pi_ = p2_ ? (f_ >= c2_) : (f_ > c2_);                                                     \
+    OI = pi_ ? f_ : c2_; OAI = pi_ ? XI : aDM_;                                                          \
   }
 
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
@@ -119,12 +132,13 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
   unsigned char* wB = wA + DP_WIN;                   // shifted by one: byte j holds the base consumed by column j
   const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
   const int max_diff = DP_GOOD * P.breaklen;
-  const int band_cap = P.band_cap, breaklen = P.breaklen;
+  const int k256 = P.one << 8;
+  const int band_cap = P.band_cap, breaklen = P.breaklen, one = P.one;
   wsync();
   // diagonal 0 is the single cell (0,0) with M = 0: its gap children open a gap, its diagonal child reads best = 0
   if (lane == 0) {
     int* b0p = bBase; int* b1p = bBase + DP_SLOTS;
-    nD[0] = DP_GOPEN; naD[0] = AUX_GAP; nI[0] = DP_GOPEN; naI[0] = AUX_GAP;
+    nD[0] = DP_GOPEN; naD[0] = 0; nI[0] = DP_GOPEN; naI[0] = 0;
     nD[DP_SMASK] = DP_NEG; nI[1] = DP_NEG;                      // halo of diagonal 0
     b0p[0] = 0; b0p[2 * DP_SLOTS] = 0; b0p[DP_SMASK] = DP_NEG; b0p[1] = DP_NEG;
     b1p[DP_SMASK] = DP_NEG; b1p[0] = DP_NEG; b1p[1] = DP_NEG; b1p[2] = DP_NEG;
@@ -160,6 +174,9 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
       const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];
       const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);
       const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];
+      // per byte c (= cell c): xm != 0 where the two bases differ, ym != 0 where they do not score as a match
+      const unsigned awr = dev_byte_rev(aw);
+      const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);
       wsync();
       if (actg) {
         int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai;
@@ -177,11 +194,11 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
         st4(cB + y, o0b, o1b, o2b, o3b); st4(cA + y, o0a, o1a, o2a, o3a);
         st4(nD + y, o0d, o1d, o2d, o3d); st4(naD + y, o0ad, o1ad, o2ad, o3ad);
         st4(nI + y, o0i, o1i, o2i, o3i); st4(naI + y, o0ai, o1ai, o2ai, o3ai);
-        int k = (o3b << 8) + r0 + 3;
+        int k = o3b * k256 + (r0 + 3);
         lkey = k > lkey ? k : lkey;
-        k = (o2b << 8) + r0 + 2; lkey = k > lkey ? k : lkey;
-        k = (o1b << 8) + r0 + 1; lkey = k > lkey ? k : lkey;
-        k = (o0b << 8) + r0; lkey = k > lkey ? k : lkey;
+        k = o2b * k256 + (r0 + 2); lkey = k > lkey ? k : lkey;
+        k = o1b * k256 + (r0 + 1); lkey = k > lkey ? k : lkey;
+        k = o0b * k256 + r0; lkey = k > lkey ? k : lkey;
       }
       wsync();
     }
@@ -227,7 +244,8 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     if (!optimal) { o.reached = 1; FinD = N + M; FinJ = M; finAux = lastAux; }
     else if (FinD == dlast) o.reached = 1;
   }
-  o.fi = FinD - FinJ; o.fj = FinJ; o.cols = finAux >> 16; o.errs = finAux & 0xffff;
+  o.fi = FinD - FinJ; o.fj = FinJ;
+  o.cols = FinD - (finAux >> 16); o.errs = (finAux & 0xffff) + FinD - 2 * (finAux >> 16);
   if (lane == 0) {
     atomic_add_u64(st.cells, cells);
     atomic_add_u64(st.calls, 1ull);
@@ -404,7 +422,11 @@ struct ExtIn {
 static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #endif
 
-MFSC_KERNEL_LB(128, 4) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st) {
+#ifndef MFSC_EXT_MINBLOCKS
+#define MFSC_EXT_MINBLOCKS 6
+#endif
+MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
+                                                   unsigned* ticket) {
 #ifdef MFSC_EMU
   int* sm = emu_dp_smem;
 #else
@@ -412,7 +434,12 @@ MFSC_KERNEL_LB(128, 4) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, 
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;
 #endif
   const int lane = lane_id();
-  for (long long q = warp_global(); q < n_reads; q += warps_total()) {
+  // reads are handed out by a ticket counter: a warp takes the next read when it is done with its own
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = (int)atomic_add_u32(ticket, 1u);
+    q = wbcast_i32(q, 0);
+    if (q >= n_reads) break;
     const int b0 = I.seg[2 * q], b1 = I.seg[2 * q + 1];
     const int n0 = I.n_pc[2 * q], n1 = I.n_pc[2 * q + 1];
     const int nC = n0 + n1;

@@ -69,6 +69,7 @@ static inline int dev_ffs64(unsigned long long x) { return x ? __builtin_ctzll(x
 static inline int dev_clz32(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int dev_clz64(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
 static inline int dev_popc32(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned dev_byte_rev(unsigned x) { return __builtin_bswap32(x); }
 static inline unsigned dev_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31u)); }
 static inline unsigned long long dev_brev64(unsigned long long x) {
   unsigned long long r = 0;
@@ -124,6 +125,7 @@ MFSC_DEV int dev_ffs64(unsigned long long x) { return __ffsll((long long)x); }
 MFSC_DEV int dev_clz32(unsigned x) { return __clz((int)x); }
 MFSC_DEV int dev_clz64(unsigned long long x) { return __clzll((long long)x); }
 MFSC_DEV int dev_popc32(unsigned x) { return __popc(x); }
+MFSC_DEV unsigned dev_byte_rev(unsigned x) { return __byte_perm(x, 0u, 0x0123u); }
 MFSC_DEV unsigned dev_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
 MFSC_DEV unsigned long long dev_brev64(unsigned long long x) { return __brevll(x); }
 MFSC_DEV unsigned ld_volatile_u32(const volatile unsigned* p) { return *p; }

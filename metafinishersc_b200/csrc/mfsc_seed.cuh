@@ -14,6 +14,7 @@ struct DevParams {
   int minmatch, mincluster, maxgap, breaklen, diagdiff, maxmatch, simplify, band_cap;
   double diagfactor;
   int k, stride;
+  int one;   // the integer 1, opaque to the compiler (see FADD in mfsc_extend.cuh)
 };
 
 struct ProbeChunk { int qs, pb, pe; };
