@@ -86,28 +86,72 @@ MFSC_DEV int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
 MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b; v.z = c; v.w = d; *reinterpret_cast<int4*>(p) = v; }
 
 // one DP cell; Dv/Iv: gap states handed over by the parents, rB/rA: best state of the diagonal parent
-// The three 3-way selections of a cell share their pairwise winners.  Tie rule of the reference DP: the
-// diagonal state wins ties, then the A-gap state, then the B-gap state.
-//   best        : I vs M  -> (vIM,aIM);  D wins iff D > vIM
-//   towards j+1 : D extends (GCONT), I/M open (GOPEN): D wins iff D+GCONT > vIM+GOPEN
-//   towards i+1 : I extends, D/M open: with (vDM,aDM) = D vs M, I wins iff I+GCONT > vDM+GOPEN, or equal when
-//                 vDM came from D (I beats D on ties but loses to M)
+// The three 3-way selections of a cell share their winners.  Tie rule of the reference DP: the diagonal state
+// wins ties, then the A-gap state (I), then the B-gap state (D).
+//   best        : I vs M -> (vIM, aIM);  D wins iff D > vIM                          -> (bv, ba), pb = "D won"
+//   towards j+1 : D extends (GCONT) or the best state opens (GOPEN): D wins iff D+GCONT > bv+GOPEN.  (When the best
+//                 state is D itself its "open" candidate D+GOPEN is below D+GCONT, so using bv is exact.)
+//   towards i+1 : I extends or the best state opens: I wins iff I+GCONT > bv+GOPEN, or on equality when the best
+//                 state is D (I beats D on ties but loses to M).
 #define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI)                                   \
   {                                                                                                      \
     const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;             \
     const int Mv_ = FADD(RB, nm_ ? DP_BAD : DP_GOOD);                                                    \
     const int xM_ = RA + (ne_ ? AUX_PAIR + 1 : AUX_PAIR);                                                \
-    const bool p1_ = IV > Mv_, p2_ = DV > Mv_;                                                           \
+    const bool p1_ = IV > Mv_;                                                                           \
     const int vIM_ = p1_ ? IV : Mv_, aIM_ = p1_ ? XI : xM_;                                              \
-    const int vDM_ = p2_ ? DV : Mv_, aDM_ = p2_ ? XD : xM_;                                              \
     const bool pb_ = DV > vIM_;                                                                          \
-    OB = pb_ ? DV : vIM_; OA = pb_ ? XD : aIM_;                                                          \
-    const int e_ = FADD(DV, DP_GCONT), c_ = FADD(vIM_, DP_GOPEN);                                        \
+    const int bv_ = pb_ ? DV : vIM_, ba_ = pb_ ? XD : aIM_;                                              \
+    OB = bv_; OA = ba_;                                                                                  \
+    const int c_ = FADD(bv_, DP_GOPEN), e_ = FADD(DV, DP_GCONT), f_ = FADD(IV, DP_GCONT);                \
     const bool pd_ = e_ > c_;                                                                            \
-    OD = pd_ ? e_ : c_; OAD = pd_ ? XD : aIM_;                                                           \
-    const int f_ = FADD(IV, DP_GCONT), c2_ = FADD(vDM_, DP_GOPEN);                                       \
-    const bool pi_ = p2_ ? (f_ >= c2_) : (f_ > c2_);                                                     \
-    OI = pi_ ? f_ : c2_; OAI = pi_ ? XI : aDM_;                                                          \
+    OD = pd_ ? e_ : c_; OAD = pd_ ? XD : ba_;                                                            \
+    const bool pi_ = (f_ > c_) || (pb_ && f_ == c_);                                                     \
+    OI = pi_ ? f_ : c_; OAI = pi_ ? XI : ba_;                                                            \
+  }
+
+// One pass of the lanes over 32 groups of four cells, highest group GT on lane 0.  B0..B3/BJ receive the lane's
+// four best-state values (DP_NEG outside the band) and the group's first j.
+#define DP_PASS(GT, B0, B1, B2, B3, BJ)                                                                                 \
+  {                                                                                                                      \
+    const bool actg = (GT) - lane >= glo;                                                                                \
+    const int g = actg ? (GT) - lane : glo;          /* idle lanes shadow the lowest group (loads only) */               \
+    const int j0 = g * 4;                                                                                                \
+    const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;                                                               \
+    const int4 vD = ld4(nD + y), vaD = ld4(naD + y), vI = ld4(nI + y), vaI = ld4(naI + y), vB = ld4(cB + y), vA = ld4(cA + y); \
+    const int sD = nD[y1], saD = naD[y1], sB = cB[y1], sA = cA[y1];                                                      \
+    const int as = d - j0 - 4;                      /* lowest A window byte of the group (cell 3) */                     \
+    const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];               \
+    const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);                                                   \
+    const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];                                                              \
+    /* per byte c (= cell c): xm != 0 where the two bases differ, ym != 0 where they do not score as a match */          \
+    const unsigned awr = dev_byte_rev(aw);                                                                               \
+    const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);                                                  \
+    wsync();                                                                                                             \
+    if (actg) {                                                                                                          \
+      int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai; \
+      DP_CELL(3, vD.z, vaD.z, vI.w, vaI.w, vB.z, vA.z, o3b, o3a, o3d, o3ad, o3i, o3ai)                                   \
+      DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai)                                   \
+      DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai)                                   \
+      DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai)                                           \
+      /* cells of the group outside [nlo, nhi] hold junk nobody reads (the halo is rewritten below), except in the */    \
+      /* best buffer, which the trim and the maximum look at */                                                          \
+      const int r0 = j0 - nlo;                                                                                           \
+      if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = DP_NEG;                                                               \
+      if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = DP_NEG;                                                               \
+      if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = DP_NEG;                                                               \
+      if ((unsigned)r0 >= (unsigned)w) o0b = DP_NEG;                                                                     \
+      st4(cB + y, o0b, o1b, o2b, o3b); st4(cA + y, o0a, o1a, o2a, o3a);                                                  \
+      st4(nD + y, o0d, o1d, o2d, o3d); st4(naD + y, o0ad, o1ad, o2ad, o3ad);                                             \
+      st4(nI + y, o0i, o1i, o2i, o3i); st4(naI + y, o0ai, o1ai, o2ai, o3ai);                                             \
+      int k = o3b * k256 + (r0 + 3);                                                                                     \
+      lkey = k > lkey ? k : lkey;                                                                                        \
+      k = o2b * k256 + (r0 + 2); lkey = k > lkey ? k : lkey;                                                             \
+      k = o1b * k256 + (r0 + 1); lkey = k > lkey ? k : lkey;                                                             \
+      k = o0b * k256 + r0; lkey = k > lkey ? k : lkey;                                                                   \
+      B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                   \
+    }                                                                                                                    \
+    wsync();                                                                                                             \
   }
 
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
@@ -162,63 +206,43 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     int* cB = bBase + (d & 1) * DP_SLOTS; int* cA = cB + 2 * DP_SLOTS;   // holds diagonal d-2, receives diagonal d
     // lane-local best of this diagonal as one key: (score << 8) | (j - nlo); out-of-band cells never enter
     int lkey = -0x7fffffff;
-    const int glo = nlo >> 2;
-    for (int gt = nhi >> 2; gt >= glo; gt -= MFSC_LANES) {
-      const bool actg = gt - lane >= glo;
-      const int g = actg ? gt - lane : glo;          // idle lanes shadow the lowest group (loads only)
-      const int j0 = g * 4;
-      const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;
-      const int4 vD = ld4(nD + y), vaD = ld4(naD + y), vI = ld4(nI + y), vaI = ld4(naI + y), vB = ld4(cB + y), vA = ld4(cA + y);
-      const int sD = nD[y1], saD = naD[y1], sB = cB[y1], sA = cA[y1];
-      const int as = d - j0 - 4;                      // lowest A window byte of the group (cell 3)
-      const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];
-      const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);
-      const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];
-      // per byte c (= cell c): xm != 0 where the two bases differ, ym != 0 where they do not score as a match
-      const unsigned awr = dev_byte_rev(aw);
-      const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);
-      wsync();
-      if (actg) {
-        int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai;
-        DP_CELL(3, vD.z, vaD.z, vI.w, vaI.w, vB.z, vA.z, o3b, o3a, o3d, o3ad, o3i, o3ai)
-        DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai)
-        DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai)
-        DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai)
-        // cells of the group that lie outside [nlo, nhi] hold junk nobody reads (the halo is rewritten below)
-        // except in the best buffer, which the trim pass and the maximum look at
-        const int r0 = j0 - nlo;
-        if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = DP_NEG;
-        if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = DP_NEG;
-        if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = DP_NEG;
-        if ((unsigned)r0 >= (unsigned)w) o0b = DP_NEG;
-        st4(cB + y, o0b, o1b, o2b, o3b); st4(cA + y, o0a, o1a, o2a, o3a);
-        st4(nD + y, o0d, o1d, o2d, o3d); st4(naD + y, o0ad, o1ad, o2ad, o3ad);
-        st4(nI + y, o0i, o1i, o2i, o3i); st4(naI + y, o0ai, o1ai, o2ai, o3ai);
-        int k = o3b * k256 + (r0 + 3);
-        lkey = k > lkey ? k : lkey;
-        k = o2b * k256 + (r0 + 2); lkey = k > lkey ? k : lkey;
-        k = o1b * k256 + (r0 + 1); lkey = k > lkey ? k : lkey;
-        k = o0b * k256 + r0; lkey = k > lkey ? k : lkey;
-      }
-      wsync();
+    const int glo = nlo >> 2, ghi = nhi >> 2;
+#ifdef MFSC_EMU
+    for (int gt = ghi; gt >= glo; gt -= MFSC_LANES) {
+      int e0, e1, e2, e3, ej;
+      DP_PASS(gt, e0, e1, e2, e3, ej)
+      (void)e0; (void)e1; (void)e2; (void)e3; (void)ej;
     }
+#else
+    // a band of at most 248 cells touches at most 63 groups: two passes of 32 lanes, the second one rarely needed.
+    // The best-state values of both passes stay in registers for the trim below.
+    int t0 = DP_NEG, t1 = DP_NEG, t2 = DP_NEG, t3 = DP_NEG, tj = 0, l0 = DP_NEG, l1 = DP_NEG, l2 = DP_NEG, l3 = DP_NEG, lj = 0;
+    DP_PASS(ghi, t0, t1, t2, t3, tj)
+    if (ghi - glo >= MFSC_LANES) { DP_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+#endif
     // diagonal maximum, ties to the larger j; its carried word is read back from the best buffer
     const int dkey = wmax_i32(lkey);
     const int dmax = dkey >> 8;
     const int dj = nlo + (dkey & 0xff);
     const int daux = cA[dj & DP_SMASK];
     lastAux = daux;
-    if (forced || dmax >= high) { high = dmax; FinD = d; FinJ = dj; finAux = daux; }
+    const bool upd = forced || dmax >= high;
+    high = upd ? dmax : high; FinD = upd ? d : FinD; FinJ = upd ? dj : FinJ; finAux = upd ? daux : finAux;
     // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
-    if (lane == 0) {
-      nD[(nlo - 1) & DP_SMASK] = DP_NEG; nI[(nhi + 1) & DP_SMASK] = DP_NEG;
-      cB[(nlo - 1) & DP_SMASK] = DP_NEG; cB[(nhi + 1) & DP_SMASK] = DP_NEG;
+    {
+      const int hidx = ((lane & 1) ? (nhi + 1) : (nlo - 1)) & DP_SMASK;
+      int* hb = (lane & 2) ? cB : ((lane & 1) ? nI : nD);
+      if (lane < 4 && lane < MFSC_LANES) hb[hidx] = DP_NEG;
+#if MFSC_LANES == 1
+      nI[(nhi + 1) & DP_SMASK] = DP_NEG; cB[(nlo - 1) & DP_SMASK] = DP_NEG; cB[(nhi + 1) & DP_SMASK] = DP_NEG;
+#endif
     }
-    wsync();
     // trim cells that fell more than max_diff below the best (narrows the next diagonal only)
     int lo = 0x7fffffff, hi = -0x7fffffff;
     const int thr = high - max_diff;
-    for (int g = glo + lane; g <= (nhi >> 2); g += MFSC_LANES) {
+#ifdef MFSC_EMU
+    wsync();
+    for (int g = glo + lane; g <= ghi; g += MFSC_LANES) {
       const int4 v = ld4(cB + ((g * 4) & DP_SMASK));
       const int j0 = g * 4;
       const unsigned m = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
@@ -228,14 +252,27 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
         if (z > hi) hi = z;
       }
     }
+#else
+    {
+      const unsigned mt = (t0 >= thr ? 1u : 0u) | (t1 >= thr ? 2u : 0u) | (t2 >= thr ? 4u : 0u) | (t3 >= thr ? 8u : 0u);
+      const unsigned ml = (l0 >= thr ? 1u : 0u) | (l1 >= thr ? 2u : 0u) | (l2 >= thr ? 4u : 0u) | (l3 >= thr ? 8u : 0u);
+      // the low pass (if any) holds smaller j than the top pass
+      const int lo_t = mt ? tj + dev_ffs32(mt) - 1 : 0x7fffffff, lo_l = ml ? lj + dev_ffs32(ml) - 1 : 0x7fffffff;
+      const int hi_t = mt ? tj + 31 - dev_clz32(mt) : -0x7fffffff, hi_l = ml ? lj + 31 - dev_clz32(ml) : -0x7fffffff;
+      lo = lo_l < lo_t ? lo_l : lo_t;
+      hi = hi_t > hi_l ? hi_t : hi_l;
+    }
+#endif
     lo = wmin_i32(lo); hi = wmax_i32(hi);
-    if (lo > hi) { lo = nhi + 1; hi = nlo - 1; }
-    while (lo <= hi && hi - lo + 2 > band_cap) { if (cB[lo & DP_SMASK] < cB[hi & DP_SMASK]) lo++; else hi--; }
-    if (lo > hi) { nlo = 1; nhi = 0; }
-    else {
-      nlo = lo > d + 1 - N ? lo : d + 1 - N;
-      int t = d + 1 < M ? d + 1 : M;
-      nhi = hi + 1 < t ? hi + 1 : t;
+    wsync();
+    const bool none = lo > hi;
+    if (!none && hi - lo + 2 > band_cap) {
+      while (lo <= hi && hi - lo + 2 > band_cap) { if (cB[lo & DP_SMASK] < cB[hi & DP_SMASK]) lo++; else hi--; }
+    }
+    {
+      const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;
+      nlo = none ? 1 : (lo > a ? lo : a);
+      nhi = none ? 0 : (hi + 1 < t ? hi + 1 : t);
     }
   }
   const int dlast = d - 1;
