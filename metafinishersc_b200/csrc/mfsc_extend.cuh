@@ -159,7 +159,12 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
 // never gives up); optimal: reaching the far corner only counts if the best score is there.
 // Each lane owns a group of four consecutive j (aligned to 4) per step: 128-bit shared loads and
 // stores, four independent cells of instruction-level parallelism.
-MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N, int M, bool forced, bool optimal) {
+MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal) {
+  // Every per-diagonal quantity (band limits, best score, finish cell) is the same on all lanes.  Passing the
+  // inputs through a warp reduction makes that visible to the compiler (CREDUX writes a uniform register), so
+  // the per-diagonal bookkeeping is scheduled on the uniform datapath instead of the saturated vector ALU pipe.
+  const int N = wmax_i32(N_), M = wmax_i32(M_);
+  const bool forced = wmax_i32(forced_ ? 1 : 0) != 0;
   const SeqStore& RS = E.RS; const SeqStore& QS = E.QS; const SeqView Av = E.A; const SeqView Bv = E.B[dir];
   const DevParams& P = E.P; const ExtStats st = E.st;
 #ifdef MFSC_EMU
@@ -175,9 +180,9 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
   unsigned char* wA = (unsigned char*)(sm + 8 * DP_SLOTS);
   unsigned char* wB = wA + DP_WIN;                   // shifted by one: byte j holds the base consumed by column j
   const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
-  const int max_diff = DP_GOOD * P.breaklen;
-  const int k256 = P.one << 8;
-  const int band_cap = P.band_cap, breaklen = P.breaklen, one = P.one;
+  const int breaklen = wmax_i32(P.breaklen), band_cap = wmax_i32(P.band_cap), one = P.one;
+  const int max_diff = DP_GOOD * breaklen;
+  const int k256 = one << 8;
   wsync();
   // diagonal 0 is the single cell (0,0) with M = 0: its gap children open a gap, its diagonal child reads best = 0
   if (lane == 0) {
@@ -267,7 +272,9 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     wsync();
     const bool none = lo > hi;
     if (!none && hi - lo + 2 > band_cap) {
-      while (lo <= hi && hi - lo + 2 > band_cap) { if (cB[lo & DP_SMASK] < cB[hi & DP_SMASK]) lo++; else hi--; }
+      int l2 = lo, h2 = hi;
+      while (l2 <= h2 && h2 - l2 + 2 > band_cap) { if (cB[l2 & DP_SMASK] < cB[h2 & DP_SMASK]) l2++; else h2--; }
+      lo = wmax_i32(l2); hi = wmax_i32(h2);      // values read from memory: hand them back as uniform
     }
     {
       const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;

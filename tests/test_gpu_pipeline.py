@@ -74,3 +74,35 @@ def test_full_size_properties(gpu_engine):
                     (L[r2.qry_id] + 1 - r2.e2).tolist(), r2.errors.tolist()))
     assert k1 == k2
     ix.free()
+
+
+def test_cfg5_scale_index(gpu_engine):
+    """BASELINE cfg 5 shape on the reference side: 100 contigs x 5 Mbp (500 Mbp index, k = 14), one read batch
+    drawn from known places.  Property: every read's longest row lands on its source contig and offset."""
+    rng = np.random.default_rng(77)
+    n_contigs, G, L, n_reads = 100, 5_000_000, 10_000, 4000
+    contigs = [datagen.random_genome(G, np.random.default_rng(5000 + c)) for c in range(n_contigs)]
+    src = rng.integers(0, n_contigs, size=n_reads)
+    reads, starts = [], []
+    for c in range(n_contigs):
+        idx = np.nonzero(src == c)[0]
+        r, st = datagen.noisy_reads(contigs[c], len(idx), L, 0.01, 0.01, np.random.default_rng(9000 + c))
+        reads += r
+        starts += [(c, int(s)) for s in st]
+    P = engine.make_params()
+    buf = np.concatenate(contigs)
+    off = np.arange(n_contigs + 1, dtype=np.int64) * G
+    ix = gpu_engine.index((buf, off), P)
+    info = ix.info()
+    assert info["k"] == 14 and info["bases"] == n_contigs * G
+    r = gpu_engine.align(ix, reads, P)
+    ix.free()
+    best = {}
+    for i in range(len(r)):
+        q = int(r.qry_id[i])
+        ln = int(r.e1[i] - r.s1[i])
+        if q not in best or ln > best[q][0]:
+            best[q] = (ln, int(r.ref_id[i]), int(r.s1[i]))
+    assert len(best) == n_reads
+    ok = sum(1 for q, (ln, c, s1) in best.items() if c == starts[q][0] and abs(s1 - 1 - starts[q][1]) <= 50 and ln > 9000)
+    assert ok == n_reads
