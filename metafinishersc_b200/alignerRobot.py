@@ -88,13 +88,13 @@ def _get_index(E, ref_path, params):
     hit = _INDEX_CACHE.get(key)
     if hit is not None:
         return hit
-    names, seqs = fasta.read_fasta(ref_path)
+    names, buf, off = fasta.read_fasta_arrays(ref_path)
     names = [n.split()[0] if n.split() else n for n in names]      # nucmer ids stop at the first blank
     while len(_INDEX_CACHE) >= _INDEX_CACHE_MAX:
         old = next(iter(_INDEX_CACHE))
         _INDEX_CACHE.pop(old)[0].free()
-    ix = E.index(seqs, params)
-    _INDEX_CACHE[key] = (ix, names, [len(s) for s in seqs])
+    ix = E.index((buf, off), params)
+    _INDEX_CACHE[key] = (ix, names, np.diff(off).tolist())
     return _INDEX_CACHE[key]
 
 
@@ -109,10 +109,10 @@ def _run_nucmer(prefix, ref_path, qry_path, params):
             os.remove(delta)
         return None
     ix, rnames, rlens = _get_index(E, ref_path, params)
-    qnames, qseqs = fasta.read_fasta(qry_path)
+    qnames, qbuf, qoff = fasta.read_fasta_arrays(qry_path)
     qnames = [n.split()[0] if n.split() else n for n in qnames]
-    rows = E.align(ix, qseqs, params)
-    rs = RowSet(rows, rnames, rlens, qnames, [len(s) for s in qseqs], ref_path, qry_path)
+    rows = E.align(ix, (qbuf, qoff), params)
+    rs = RowSet(rows, rnames, rlens, qnames, np.diff(qoff).tolist(), ref_path, qry_path)
     while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX:
         _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)))
     _ROWS_CACHE[delta] = rs

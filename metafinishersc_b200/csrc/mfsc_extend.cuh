@@ -53,6 +53,7 @@ struct RowsOut {
 
 struct ExtCtx {
   SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
+  mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw;   // per-warp statistics, flushed once per kernel
   SeqView A; SeqView B[2];
   RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
   const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
@@ -75,7 +76,8 @@ MFSC_DEV void best3(int d, int i, int m, int ad, int ai, int am, int& v, int& a)
 // decode local positions [from, from + DP_FILL) of a sequence walk (position t -> seq pos s0 + dirn*t, 1-based);
 // the code of position t is stored at window byte t + off
 MFSC_DEV void dp_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_local, int from, int off, unsigned char* win, int lane) {
-  for (int t = from + lane; t < from + DP_FILL; t += MFSC_LANES) {
+  const int to = from + DP_FILL < n_local + 8 ? from + DP_FILL : n_local + 8;   // a few invalid codes past the end, never more
+  for (int t = from + lane; t < to; t += MFSC_LANES) {
     int c = 4;
     if (t < n_local) c = code_at(S, V.base + (unsigned)(s0 + dirn * t - 1));
     win[(t + off) & DP_WMASK] = (unsigned char)c;
@@ -166,7 +168,7 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
   const int N = wmax_i32(N_), M = wmax_i32(M_);
   const bool forced = wmax_i32(forced_ ? 1 : 0) != 0;
   const SeqStore& RS = E.RS; const SeqStore& QS = E.QS; const SeqView Av = E.A; const SeqView Bv = E.B[dir];
-  const DevParams& P = E.P; const ExtStats st = E.st;
+  const DevParams& P = E.P;
 #ifdef MFSC_EMU
   int* sm = E.sm;
 #else
@@ -291,9 +293,8 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
   o.fi = FinD - FinJ; o.fj = FinJ;
   o.cols = FinD - (finAux >> 16); o.errs = (finAux & 0xffff) + FinD - 2 * (finAux >> 16);
   if (lane == 0) {
-    atomic_add_u64(st.cells, cells);
-    atomic_add_u64(st.calls, 1ull);
-    if (maxw > *st.max_band) atomic_max_i32(st.max_band, maxw);
+    E.acc_cells += cells; E.acc_calls += 1ull;
+    if (maxw > E.acc_maxw) E.acc_maxw = maxw;
   }
   return o;
 }
@@ -478,6 +479,7 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;
 #endif
   const int lane = lane_id();
+  unsigned long long w_cells = 0, w_calls = 0; int w_maxw = 0;
   // reads are handed out by a ticket counter: a warp takes the next read when it is done with its own
   for (;;) {
     int q = 0;
@@ -528,6 +530,7 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
     wsync();
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
+    E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0;
     E.B[0].base = QS.start[2 * q]; E.B[0].n = QS.len[2 * q];
     E.B[1].base = QS.start[2 * q + 1]; E.B[1].n = QS.len[2 * q + 1];
     E.pc_rc0 = b1; E.pc_first = I.pc_first; E.pc_n = I.pc_n; E.fused = I.fused;
@@ -553,6 +556,12 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
       if (R.dir[row0 + x]) { R.sB[row0 + x] = qlen - R.sB[row0 + x] + 1; R.eB[row0 + x] = qlen - R.eB[row0 + x] + 1; }
     }
     if (lane == 0) R.n_rows[q] = rows;
+    w_cells += E.acc_cells; w_calls += E.acc_calls; if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
+  }
+  if (lane == 0 && w_calls) {
+    atomic_add_u64(st.cells, w_cells);
+    atomic_add_u64(st.calls, w_calls);
+    atomic_max_i32(st.max_band, w_maxw);
   }
 }
 

@@ -31,6 +31,43 @@ def read_fasta(path):
     return names, seqs
 
 
+def read_fasta_arrays(path):
+    """Vectorised ingest for the aligner: -> (names list[str], uint8 bases, int64 offsets[n+1]).
+    Same records as read_fasta (blank lines skipped, sequence lines joined), without per-line Python work."""
+    data = np.fromfile(path, dtype=np.uint8)
+    if data.size == 0:
+        return [], np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+    nl = np.flatnonzero(data == 10)
+    starts = np.concatenate(([0], nl + 1))
+    ends = np.concatenate((nl, [data.size]))
+    if starts[-1] >= data.size:                       # file ends with a newline
+        starts, ends = starts[:-1], ends[:-1]
+    ends = ends - ((ends > starts) & (data[np.maximum(ends - 1, 0)] == 13))      # strip \r
+    nonempty = ends > starts
+    starts, ends = starts[nonempty], ends[nonempty]
+    is_hdr = data[starts] == 62
+    hdr_idx = np.flatnonzero(is_hdr)
+    if hdr_idx.size == 0:
+        return [], np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+    raw = data.tobytes()
+    names = [raw[starts[i] + 1:ends[i]].decode() for i in hdr_idx]
+    # sequence lines before the first header are ignored (read_fasta does the same)
+    seq_mask = ~is_hdr
+    seq_mask[:hdr_idx[0]] = False
+    lens = np.where(seq_mask, ends - starts, 0)
+    # record of each line = number of headers seen so far - 1
+    rec_of_line = np.cumsum(is_hdr) - 1
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    np.add.at(off, rec_of_line[seq_mask] + 1, lens[seq_mask])
+    np.cumsum(off, out=off)
+    # gather the bases: byte-level keep mask from a +1/-1 difference array over line spans
+    diff = np.zeros(data.size + 1, dtype=np.int8)
+    np.add.at(diff, starts[seq_mask], 1)
+    np.add.at(diff, ends[seq_mask], -1)
+    keep = np.cumsum(diff[:-1], dtype=np.int8).astype(bool)
+    return names, np.ascontiguousarray(data[keep]), off
+
+
 def write_fasta(path, names, seqs, line_len=0):
     with open(path, "wb") as f:
         for n, s in zip(names, seqs):
