@@ -81,6 +81,7 @@ static inline unsigned long long ld_volatile_u64(const volatile unsigned long lo
 static inline void st_volatile_u64(volatile unsigned long long* p, unsigned long long v) { *p = v; }
 static inline void dev_threadfence() {}
 template <class T> static inline T ldg(const T* p) { return *p; }
+template <class T> static inline T ld_stream(const T* p) { return *p; }
 
 #else
 // ------------------------------------------------------------------------------------------
@@ -133,6 +134,8 @@ MFSC_DEV unsigned long long ld_volatile_u64(const volatile unsigned long long* p
 MFSC_DEV void st_volatile_u64(volatile unsigned long long* p, unsigned long long v) { *p = v; }
 MFSC_DEV void dev_threadfence() { __threadfence(); }
 template <class T> MFSC_DEV T ldg(const T* p) { return __ldg(p); }
+// streaming load: evict-first in L2, so a one-touch random stream does not displace the reused tables
+template <class T> MFSC_DEV T ld_stream(const T* p) { return __ldcs(p); }
 #endif
 
 // common helpers --------------------------------------------------------------------------

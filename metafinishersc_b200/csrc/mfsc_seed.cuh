@@ -54,7 +54,9 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, con
       const unsigned qp = qstart + (unsigned)p;
       if (win32(Q.inv, qp) & vmask) continue;
       const unsigned long long km = win64(Q.txt, qp) & kmask;
-      const unsigned b0 = H[km], b1 = H[km + 1];
+      // the bucket heads (1/4 GB and up) are touched once per probe at random: stream them through L2 so that the
+      // position table and the packed reference text, which every candidate re-reads, stay resident
+      const unsigned b0 = ld_stream(&H[km]), b1 = ld_stream(&H[km + 1]);
       for (unsigned h = b0; h < b1; h++) {
         const unsigned r = pos[h];
         const int maxl = p < s ? p : s;
