@@ -111,16 +111,25 @@ def oracle_rate(contigs, reads, threads):
     return bases / dt / 1e6, dt, sum(res)
 
 
+def size_sample(contigs, reads, threads, target_s):
+    """Reads per sample so that the oracle runs about target_s on `threads` threads: two pilots fit
+    time = fixed (per-thread index build) + per-read cost."""
+    n1, n2 = 2 * threads, 8 * threads
+    _, t1, _ = oracle_rate(contigs, reads[:n1], threads)
+    _, t2, _ = oracle_rate(contigs, reads[:n2], threads)
+    b = max((t2 - t1) / (n2 - n1), 1e-6)
+    a = max(t1 - b * n1, 0.0)
+    return int(max(threads, min(len(reads), (target_s - a) / b)))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    contigs, reads = make_workload(0, max(64, min(args.reads, 4 * threads)), args.genome)
-    # pilot to size the per-step sample (~ args.ref_step_seconds of CPU work on all threads)
-    rate, dt, _ = oracle_rate(contigs, reads[:2 * threads], threads)
-    per_read_s = dt / (2 * threads)
-    n_sample = int(max(threads, min(args.reads, args.ref_step_seconds / per_read_s)))
-    contigs, reads = make_workload(0, n_sample, args.genome)
+    contigs, reads = make_workload(0, args.reads, args.genome)
+    # pilots size the per-step sample (~ args.ref_step_seconds of CPU work on all threads)
+    n_sample = size_sample(contigs, reads, threads, args.ref_step_seconds)
+    reads = reads[:n_sample]
     for _ in range(args.warmup):
         oracle_rate(contigs, reads[:threads], threads)
     total_dt, total_bases, cells = 0.0, 0, 0
@@ -294,10 +303,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            pilot = reads[:4 * threads]
-            oracle_rate(contigs, pilot[:threads], threads)       # warm the thread pool and the oracle's index build path
-            _, dt, _ = oracle_rate(contigs, pilot, threads)
-            n_s = int(max(threads, min(len(reads), args.cpu_seconds / (dt / len(pilot)))))
+            n_s = size_sample(contigs, reads, threads, args.cpu_seconds)
             v, dt, c = oracle_rate(contigs, reads[:n_s], threads)
             out["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": threads, "kind": "port",
                                    "sample": "first %d reads of the batch (%.1f s), CPU oracle restatement (MUMmer not in image)" % (n_s, dt),
