@@ -3,7 +3,6 @@
 // rooflines.  (tests/emu builds this same file with -DMFSC_EMU for CPU-side logic tests.)
 #include "../../include/mfsc.h"
 #include "mfsc_extend.cuh"
-#include "mfsc_extend_tiled.cuh"
 #include "mfsc_coverage.cuh"
 
 #include <algorithm>
@@ -604,23 +603,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
 #endif
       // persistent grid: as many blocks as are resident at once, reads handed out by ticket
       unsigned* ext_ticket = (unsigned*)(d_stats + 3);
-      static const bool use_tiled = []() { const char* e = getenv("MFSC_EXT_KERNEL"); return e && strcmp(e, "tiled") == 0; }();
-      if (use_tiled) {
-        // several reads per warp (mfsc_extend_tiled.cuh)
-        const int xt_block = XT >= 4 ? 64 : 128;
-        const size_t xt_smem = (size_t)(xt_block / MFSC_LANES) * XT * XT_TILE_INTS * sizeof(int);
-        const long long xt_threads = ((long long)n_reads + XT - 1) / XT * MFSC_LANES;
-        unsigned xt_grid = grid_for(D, xt_threads, xt_block, 3);
-#ifndef MFSC_EMU
-        cudaFuncSetAttribute(k_extend_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xt_smem);
-        {
-          int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend_tiled, xt_block, xt_smem) == cudaSuccess && occ > 0)
-            xt_grid = grid_for(D, xt_threads, xt_block, occ);
-        }
-#endif
-        MFSC_LAUNCH(k_extend_tiled, xt_grid, xt_block, xt_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket);
-      } else {
+      {
         unsigned ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 4);
 #ifndef MFSC_EMU
         {
