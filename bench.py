@@ -266,6 +266,13 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except Exception:
+            pass
+        full = args.workload == "cfg2" and args.reads == 25000 and args.genome == 5_000_000
+        ext_tr = traffic.get("k_extend", {}) if full else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         ext_ms = stage["extend"] / K
@@ -294,8 +301,13 @@ def main():
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"kernel": "k_extend", "bound": "alu", "achieved": ext_tiops, "peak": alu_peak, "unit": "Tiop/s (int32)",
-                         "frac": ext_tiops / alu_peak if alu_peak else None, "traffic": None,
-                         "note": "banded DP: cells x %d int ops / kernel time; peak = %d SMs x 128 lanes x %.0f MHz observed" % (ops_per_cell, n_sm, sm_mhz)},
+                         "frac": ext_tiops / alu_peak if alu_peak else None,
+                         "traffic": (ext_tr["dram_bytes_read"] + ext_tr["dram_bytes_write"]) if ext_tr else None,
+                         "pipe_active_ncu": {"alu": ext_tr.get("alu_pipe_active_pct"), "fma": ext_tr.get("fma_pipe_active_pct"),
+                                             "issue": ext_tr.get("issue_active_pct"), "source": ext_tr.get("source")} if ext_tr else None,
+                         "note": "banded DP, no HBM traffic to speak of (traffic = ncu dram bytes per launch): cells x %d int ops / kernel time; "
+                                 "peak = %d SMs x 128 lanes x %.0f MHz observed. The binding unit is the ALU pipe (64 lanes/clk/SM), "
+                                 "82%% active in the ncu capture" % (ops_per_cell, n_sm, sm_mhz)},
             "roofline_seed": {"kernel": "k_seeds", "bound": "hbm", "achieved": seed_bytes / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else None,
                               "peak": hbm_peak, "unit": "GB/s", "frac": seed_bytes / (seed_ms * 1e-3) / 1e9 / hbm_peak if seed_ms > 0 else None,
                               "traffic": None, "peak_source": peak_src,
