@@ -56,6 +56,14 @@ def build_cases(scale=1):
     flank = datagen.random_genome(4000, np.random.default_rng(10)).tobytes()
     tandem = flank[:2000] + unit * 40 + flank[2000:]
     cases.append(("tandem_repeat", [tandem], [flank[1500:2000] + unit * 25 + flank[2000:2400], rc(tandem[1000:3500])], {}))
+    # the DP band limit (band_cap) actually binding, and extensions longer than the 10 000-base DP limit
+    cases.append(("band_cap_64", d2["contigs"], d2["reads"][:6], dict(band_cap=64)))
+    long_reads, _ = datagen.noisy_reads(np.frombuffer(d["contigs"][0], dtype=np.uint8), 6, 26_000, 0.01, 0.01, np.random.default_rng(31))
+    cases.append(("reads_longer_than_dp_limit", d["contigs"], [long_reads[0], rc(long_reads[1])] + long_reads[2:], {}))
+    # 2000 identical reference records: every read has 2000 clusters, and the first match buffer overflows (retry path)
+    unit300 = datagen.random_genome(300, np.random.default_rng(12)).tobytes()
+    many = [unit300] * 2000
+    cases.append(("many_identical_records", many, [unit300, rc(unit300), unit300[10:280]] * 14, {}))
     cases.append(("explicit_kmer_8", d["contigs"], mixed[:40], dict(kmer=8)))
     cases.append(("explicit_kmer_14", d["contigs"], mixed[:40], dict(kmer=14)))
     return cases
@@ -65,7 +73,8 @@ def run_case(E, O, ref, qry, opts):
     """Run one case through engine E and the oracle O; returns a list of mismatch descriptions."""
     from metafinishersc_b200 import engine
     okw = {k: v for k, v in opts.items() if k != "kmer"}
-    o = O.align(ref, qry, band_cap=248, **okw)
+    okw.setdefault("band_cap", 248)
+    o = O.align(ref, qry, **okw)
     P = engine.make_params(**opts)
     ix = E.index(ref, P)
     r = E.align(ix, qry, P, flags=engine.KEEP_MEMS | engine.KEEP_CLUSTERS)
