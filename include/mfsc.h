@@ -82,6 +82,8 @@ int mfsc_reads_free(mfsc_reads* r);
 #define MFSC_KEEP_CLUSTERS 2   /* keep the clusters for mfsc_result_clusters */
 #define MFSC_STOP_SEEDS 4      /* stop after stage 2 */
 #define MFSC_STOP_CLUSTERS 8   /* stop after stage 3 */
+#define MFSC_WANT_DELTAS 16    /* also produce the delta (indel offset) list of every row: runs the traceback-recording
+                                  instantiation of the extension kernel, about 2x slower and 5 MB of HBM per resident warp */
 
 /* stages 2-4 on a resident batch */
 int mfsc_align_reads(mfsc_index* ix, mfsc_reads* reads, const mfsc_params* p, int32_t flags, mfsc_result** out);
@@ -93,6 +95,7 @@ int mfsc_align_batch(mfsc_index* ix, const uint8_t* bases, const int64_t* read_o
 #define MFSC_N_MEMS 1
 #define MFSC_N_CLUSTERS 2
 #define MFSC_N_CLUSTER_MATCHES 3
+#define MFSC_N_DELTAS 4
 int64_t mfsc_result_count(const mfsc_result* r, int32_t what);
 /* rows in delta order (read, then contig, then cluster walk); s2/e2 on the forward read, s2 > e2 for
  * reverse-strand rows; errors/cols give %IDY = 100*(cols-errors)/cols as show-coords computes it */
@@ -105,6 +108,9 @@ int mfsc_result_mems(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int
  * matches: s1, s2, len as above */
 int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand, int32_t* rec, int32_t* first,
                          int32_t* count, int64_t* m_s1, int32_t* m_s2, int32_t* m_len);
+/* delta lists (MFSC_WANT_DELTAS): row i owns deltas[begin[i] .. end[i]), MUMmer's signed distances to the next
+ * indel (positive: reference base without partner, negative: read base without partner) */
+int mfsc_result_deltas(const mfsc_result* r, int64_t* begin, int64_t* end, int32_t* deltas);
 /* stats[16]: 0 DP cells, 1 DP calls, 2 widest band, 3 probes, 4 matches, 5 kernel launches,
  * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes;
  * ms[16]: 0 upload+pack, 1 seeds, 2 sort, 3 cluster, 4 extend, 5 compact+download, 6 total */
@@ -118,9 +124,10 @@ int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, i
 
 /* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
  * delta file of a row set.  names: NUL-separated, one per record.  The delta carries the alignment
- * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors cols`) but no indel offset list: the
- * traceback-free DP does not produce one, so the 7th header field holds the alignment column count
- * (MUMmer writes stop codons there, always 0 for nucmer) to keep %IDY reproducible from the file. */
+ * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors 0`) followed by the indel offset list when the
+ * batch was aligned with MFSC_WANT_DELTAS.  Without it (the default, traceback-free DP) the list is empty and
+ * the 7th header field holds the alignment column count (MUMmer writes stop codons there, always 0 for nucmer)
+ * so that %IDY stays reproducible from the file. */
 int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
                       const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
                       const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
@@ -129,7 +136,8 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
                      const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
                      const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,
                      const char* ref_names, const int32_t* ref_len, int32_t n_ref,
-                     const char* qry_names, const int32_t* qry_len, int32_t n_qry);
+                     const char* qry_names, const int32_t* qry_len, int32_t n_qry,
+                     const int64_t* d_begin, const int64_t* d_end, const int32_t* deltas /* all three NULL: headers only */);
 
 #ifdef __cplusplus
 }

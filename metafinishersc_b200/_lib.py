@@ -32,14 +32,14 @@ def make_params(minmatch=20, mincluster=65, maxgap=90, breaklen=200, diagdiff=5,
     return p
 
 
-KEEP_MEMS, KEEP_CLUSTERS, STOP_SEEDS, STOP_CLUSTERS = 1, 2, 4, 8
+KEEP_MEMS, KEEP_CLUSTERS, STOP_SEEDS, STOP_CLUSTERS, WANT_DELTAS = 1, 2, 4, 8, 16
 
 # every symbol include/mfsc.h declares (tests check the library exports all of them)
 SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_device", "mfsc_default_params",
            "mfsc_host_alloc", "mfsc_host_free", "mfsc_index_build", "mfsc_index_create", "mfsc_index_info",
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_reads_upload", "mfsc_reads_free",
            "mfsc_align_reads", "mfsc_align_batch", "mfsc_result_count", "mfsc_result_rows", "mfsc_result_mems",
-           "mfsc_result_clusters", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_write_coords",
+           "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_write_coords",
            "mfsc_write_delta"]
 
 
@@ -72,13 +72,14 @@ def bind(path):
     L.mfsc_result_rows.argtypes = [c_vp] * 9
     L.mfsc_result_mems.argtypes = [c_vp] * 6
     L.mfsc_result_clusters.argtypes = [c_vp] * 9
+    L.mfsc_result_deltas.argtypes = [c_vp, c_vp, c_vp, c_vp]
     L.mfsc_result_stats.argtypes = [c_vp, c_vp, c_vp]
     L.mfsc_result_free.argtypes = [c_vp]
     L.mfsc_coverage.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]
     L.mfsc_write_coords.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_i32, ctypes.c_char_p, c_i32, c_i32]
     L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
-        [ctypes.c_char_p, c_vp, c_i32, ctypes.c_char_p, c_vp, c_i32]
+        [ctypes.c_char_p, c_vp, c_i32, ctypes.c_char_p, c_vp, c_i32, c_vp, c_vp, c_vp]
     return L
 
 

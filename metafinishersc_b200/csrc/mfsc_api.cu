@@ -276,6 +276,8 @@ struct mfsc_result {
   std::vector<int> m_q, m_strand, m_s2, m_len; std::vector<long long> m_s1;
   // clusters (host, optional)
   std::vector<int> c_q, c_strand, c_rec, c_first, c_n, cm_s2, cm_len; std::vector<long long> cm_s1;
+  // delta lists (host, optional): per row [begin, end) into deltas, -1 when unavailable
+  std::vector<int> dl_b, dl_e, deltas;
   long long n_mems = 0;
   int64_t stats[16]; double ms[16];
 };
@@ -586,6 +588,8 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     if (!(flags & MFSC_STOP_CLUSTERS)) {
       // ---- stage 4: extension ----
       RowsOut R0, R1;
+      const bool want_deltas = (flags & MFSC_WANT_DELTAS) != 0;
+      memset(&R0, 0, sizeof(R0)); memset(&R1, 0, sizeof(R1));
       DA(int, r_ref, M); DA(int, r_qry, M); DA(int, r_dir, M); DA(int, r_sA, M); DA(int, r_eA, M); DA(int, r_sB, M); DA(int, r_eB, M);
       DA(int, r_errs, M); DA(int, r_cols, M); DA(int, r_n, n_reads); DA(int, r_off, n_reads + 1);
       DA(int, x_ord, M); DA(int, x_tmp, M); DA(int, x_grp, M); DA(unsigned char, x_fused, M);
@@ -599,20 +603,47 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       const int ext_block = 128;
       const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
 #ifndef MFSC_EMU
-      cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem);
+      cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem);
 #endif
       // persistent grid: as many blocks as are resident at once, reads handed out by ticket
       unsigned* ext_ticket = (unsigned*)(d_stats + 3);
-      {
+      TbPool pool; pool.tb = nullptr; pool.rev = nullptr; pool.arena = nullptr;
+      DeltaOut DO; DO.buf = nullptr; DO.used = nullptr; DO.cap = 0; DO.n_bad = nullptr;
+      if (!want_deltas) {
         unsigned ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 4);
 #ifndef MFSC_EMU
         {
           int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, ext_block, ext_smem) == cudaSuccess && occ > 0)
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, ext_block, ext_smem) == cudaSuccess && occ > 0)
             ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, occ);
         }
 #endif
-        MFSC_LAUNCH(k_extend, ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket);
+        MFSC_LAUNCH(k_extend<false>, ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+      } else {
+        // delta mode: the kernel instantiation that records one traceback byte per cell (mfsc_extend.cuh)
+#ifdef MFSC_EMU
+        const int tb_block = 32; unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 1);
+        const size_t tb_smem = 0;
+#else
+        const int tb_block = ext_block; const size_t tb_smem = ext_smem;
+        cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem);
+        unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 4);
+        {
+          int occ = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true>, tb_block, tb_smem) == cudaSuccess && occ > 0)
+            tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, occ);
+        }
+#endif
+        const size_t n_warps = (size_t)tb_grid * (tb_block / MFSC_LANES);
+        DA(unsigned char, p_tb, n_warps * TB_DIAGS * DP_SLOTS); DA(unsigned char, p_rev, n_warps * TB_DIAGS); DA(int, p_arena, n_warps * TB_ARENA_INTS);
+        DA(int, x_head, M); DA(int, x_tail, M); DA(int, x_dlb, M); DA(int, x_dle, M);
+        const long long dcap = rd->q.n_bases / 2 + (1 << 20);
+        DA(int, d_delta, dcap); DA(unsigned long long, d_used, 2);
+        D.zero(d_used, sizeof(unsigned long long) * 2);
+        pool.tb = p_tb; pool.rev = p_rev; pool.arena = p_arena;
+        DO.buf = d_delta; DO.used = d_used; DO.cap = dcap; DO.n_bad = (unsigned*)(d_used + 1);
+        R0.head = x_head; R0.tail = x_tail; R0.dl_begin = x_dlb; R0.dl_end = x_dle;
+        MFSC_LAUNCH(k_extend<true>, tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
       }
       D.launches++;
       stamp(D, ts[4]);
@@ -623,6 +654,12 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       n_rows = total;
       DA(int, c_ref, n_rows); DA(int, c_qry, n_rows); DA(int, c_dir, n_rows); DA(int, c_sA, n_rows); DA(int, c_eA, n_rows); DA(int, c_sB, n_rows);
       DA(int, c_eB, n_rows); DA(int, c_errs, n_rows); DA(int, c_cols, n_rows);
+      int *c_dlb = nullptr, *c_dle = nullptr;
+      if (want_deltas) {
+        c_dlb = (int*)keep(D.alloc(sizeof(int) * (size_t)(n_rows + 1))); c_dle = (int*)keep(D.alloc(sizeof(int) * (size_t)(n_rows + 1)));
+        if (!c_dlb || !c_dle) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (delta ranges)"); }
+      }
+      R1.dl_begin = c_dlb; R1.dl_end = c_dle;
       R1.ref = c_ref; R1.qry = c_qry; R1.dir = c_dir; R1.sA = c_sA; R1.eA = c_eA; R1.sB = c_sB; R1.eB = c_eB; R1.errs = c_errs; R1.cols = c_cols; R1.n_rows = r_n;
       MFSC_LAUNCH(k_compact_rows, grid_for(D, (long long)n_reads * MFSC_LANES, 128, 16), 128, 0, D.stream, R0, seg, r_off, n_reads, R1);
       D.launches++;
@@ -632,6 +669,14 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       D.d2h(res->s1.data(), c_sA, sizeof(int) * n_rows); D.d2h(res->e1.data(), c_eA, sizeof(int) * n_rows);
       D.d2h(res->s2.data(), c_sB, sizeof(int) * n_rows); D.d2h(res->e2.data(), c_eB, sizeof(int) * n_rows);
       D.d2h(res->errs.data(), c_errs, sizeof(int) * n_rows); D.d2h(res->cols.data(), c_cols, sizeof(int) * n_rows);
+      if (want_deltas) {
+        unsigned long long used[2] = {0, 0};
+        D.d2h(used, DO.used, sizeof(used));
+        if ((unsigned)(used[1] & 0xffffffffull) != 0 || (long long)used[0] > DO.cap) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "delta lists: token arena or delta buffer too small for this batch"); }
+        res->deltas.resize(used[0]); res->dl_b.resize(n_rows); res->dl_e.resize(n_rows);
+        D.d2h(res->deltas.data(), DO.buf, sizeof(int) * used[0]);
+        D.d2h(res->dl_b.data(), c_dlb, sizeof(int) * n_rows); D.d2h(res->dl_e.data(), c_dle, sizeof(int) * n_rows);
+      }
       unsigned long long hst[4];
       D.d2h(hst, d_stats, sizeof(hst));
       res->stats[0] = (int64_t)hst[0]; res->stats[1] = (int64_t)hst[1]; res->stats[2] = (int64_t)(int)(hst[2] & 0xffffffffull);
@@ -676,6 +721,7 @@ int64_t mfsc_result_count(const mfsc_result* r, int32_t what) {
     case MFSC_N_MEMS: return (int64_t)r->m_q.size();
     case MFSC_N_CLUSTERS: return (int64_t)r->c_q.size();
     case MFSC_N_CLUSTER_MATCHES: return (int64_t)r->cm_s1.size();
+    case MFSC_N_DELTAS: return (int64_t)r->deltas.size();
   }
   return -1;
 }
@@ -700,6 +746,13 @@ int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand,
   if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
   copy_out(qry_id, r->c_q); copy_out(strand, r->c_strand); copy_out(rec, r->c_rec); copy_out(first, r->c_first); copy_out(count, r->c_n);
   copy_out(m_s1, r->cm_s1); copy_out(m_s2, r->cm_s2); copy_out(m_len, r->cm_len);
+  return MFSC_OK;
+}
+
+int mfsc_result_deltas(const mfsc_result* r, int64_t* begin, int64_t* end, int32_t* deltas) {
+  if (!r) return fail(MFSC_ERR_ARG, "result is NULL");
+  if (r->dl_b.size() != r->ref.size()) return fail(MFSC_ERR_ARG, "the batch was aligned without MFSC_WANT_DELTAS");
+  copy_out(begin, r->dl_b); copy_out(end, r->dl_e); copy_out(deltas, r->deltas);
   return MFSC_OK;
 }
 
@@ -798,7 +851,8 @@ int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_pa
 
 int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id,
                      const int32_t* s1, const int32_t* e1, const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols, const char* ref_names,
-                     const int32_t* ref_len, int32_t n_ref, const char* qry_names, const int32_t* qry_len, int32_t n_qry) {
+                     const int32_t* ref_len, int32_t n_ref, const char* qry_names, const int32_t* qry_len, int32_t n_qry,
+                     const int64_t* d_begin, const int64_t* d_end, const int32_t* deltas) {
   if (!path || n_rows < 0) return fail(MFSC_ERR_ARG, "mfsc_write_delta: bad arguments");
   std::vector<const char*> rn = split_names(ref_names, n_ref), qn = split_names(qry_names, n_qry);
   FILE* f = fopen(path, "w");
@@ -810,8 +864,15 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
       fprintf(f, ">%s %s %d %d\n", rn[ref_id[i]], qn[qry_id[i]], ref_len[ref_id[i]], qry_len[qry_id[i]]);
       last_r = ref_id[i]; last_q = qry_id[i];
     }
-    // header line of one alignment; the indel offset list is not produced by the traceback-free DP
-    fprintf(f, "%d %d %d %d %d %d %d\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i], cols[i]);
+    if (deltas && d_begin && d_begin[i] >= 0) {
+      // a real MUMmer delta record: header, signed distances to the next indel, terminating 0
+      fprintf(f, "%d %d %d %d %d %d 0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i]);
+      for (int64_t k = d_begin[i]; k < d_end[i]; k++) fprintf(f, "%d\n", deltas[k]);
+      fprintf(f, "0\n");
+    } else {
+      // header only (the default traceback-free DP produces no indel list); the 7th field carries the column count
+      fprintf(f, "%d %d %d %d %d %d %d\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i], cols[i]);
+    }
   }
   fclose(f);
   return MFSC_OK;

@@ -6,9 +6,10 @@
 // targets and drops shadowed clusters is scalar and warp-uniform; the work is the banded
 // anti-diagonal DP (nucleotide scores +3 / -7, affine gaps -7 open / -4 extend, three states per
 // cell) whose band is spread over the lanes.  Per cell the DP also carries the number of
-// alignment columns and errors of the path that produced each state, so no traceback matrix is
-// written: the row arithmetic show-coords needs (S1 E1 S2 E2, errors, columns) falls out of the
-// finish cell.
+// diagonal columns and mismatches of the path that produced each state, so no traceback matrix is
+// needed for the rows: the arithmetic show-coords needs (S1 E1 S2 E2, errors, columns) falls out of the
+// finish cell.  Only when the caller wants the delta indel lists does the TB = true instantiation record
+// one byte per cell in HBM and walk it back (see TbCtx below).
 //
 // Band state lives in shared memory (9 KB per warp), indexed circularly by the B coordinate j and
 // updated in place.  A cell does not store its three states: it stores what its two gap children
@@ -38,7 +39,7 @@
 // integer add issued as a multiply-add with a run-time 1: goes to the FMA pipe instead of the (saturated) ALU pipe
 #define FADD(a, b) ((a) * one + (b))
 
-struct DpOut { int reached, fi, fj, cols, errs; };
+struct DpOut { int reached, fi, fj, cols, errs, n_ops; };
 
 struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max_band; };
 
@@ -49,11 +50,28 @@ struct RowsOut {
   // alignments of a read are written into the read's slice (first match index of its forward strand)
   int* ref; int* qry; int* dir; int* sA; int* eA; int* sB; int* eB; int* errs; int* cols;
   int* n_rows;  // [n_reads]
+  // delta mode only: token list of each alignment (arena offsets) and the slice of the delta buffer it was written to
+  int* head; int* tail; int* dl_begin; int* dl_end;
 };
+
+// Delta (indel offset list) support.  The DP itself never needs a traceback (see the header); when the caller
+// asks for the delta lists a second instantiation of the kernel (TB = true) also writes one byte per cell --
+// best state, "D extended", "I extended" -- into a per-warp buffer in HBM, walks it back from the finish cell
+// after each DP that contributes columns to an alignment, and keeps every alignment as a linked list of token
+// chunks (run of diagonal columns >= 0, -1 = column consuming A only, -2 = column consuming B only).
+#define TB_DIAGS (2 * DP_MAX_ALN + 8)
+#define TB_ARENA_INTS (1 << 16)
+struct TbCtx {
+  unsigned char* tb;    // [TB_DIAGS * DP_SLOTS] codes of the current DP, row d, column j & DP_SMASK
+  unsigned char* rev;   // [TB_DIAGS] columns of the last traceback, last column first (0 diagonal, 1 A only, 2 B only)
+  int* arena; int top; int bad;
+};
+struct DeltaOut { int* buf; unsigned long long* used; long long cap; unsigned* n_bad; };
 
 struct ExtCtx {
   SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
   mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw;   // per-warp statistics, flushed once per kernel
+  mutable TbCtx T;
   SeqView A; SeqView B[2];
   RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
   const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
@@ -95,7 +113,7 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
 //                 state is D itself its "open" candidate D+GOPEN is below D+GCONT, so using bv is exact.)
 //   towards i+1 : I extends or the best state opens: I wins iff I+GCONT > bv+GOPEN, or on equality when the best
 //                 state is D (I beats D on ties but loses to M).
-#define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI)                                   \
+#define DP_CELL(C, DV, XD, IV, XI, RB, RA, OB, OA, OD, OAD, OI, OAI, OT)                               \
   {                                                                                                      \
     const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;             \
     const int Mv_ = FADD(RB, nm_ ? DP_BAD : DP_GOOD);                                                    \
@@ -110,6 +128,8 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
     OD = pd_ ? e_ : c_; OAD = pd_ ? XD : ba_;                                                            \
     const bool pi_ = (f_ > c_) || (pb_ && f_ == c_);                                                     \
     OI = pi_ ? f_ : c_; OAI = pi_ ? XI : ba_;                                                            \
+    /* traceback code: bits 0-1 best state (0 D, 1 I, 2 M), bit 2 D extended towards j+1, bit 3 I extended towards i+1 */ \
+    OT = (pb_ ? 0u : (p1_ ? 1u : 2u)) | (pd_ ? 4u : 0u) | (pi_ ? 8u : 0u);                              \
   }
 
 // One pass of the lanes over 32 groups of four cells, highest group GT on lane 0.  B0..B3/BJ receive the lane's
@@ -132,10 +152,11 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
     wsync();                                                                                                             \
     if (actg) {                                                                                                          \
       int o0b, o0a, o0d, o0ad, o0i, o0ai, o1b, o1a, o1d, o1ad, o1i, o1ai, o2b, o2a, o2d, o2ad, o2i, o2ai, o3b, o3a, o3d, o3ad, o3i, o3ai; \
-      DP_CELL(3, vD.z, vaD.z, vI.w, vaI.w, vB.z, vA.z, o3b, o3a, o3d, o3ad, o3i, o3ai)                                   \
-      DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai)                                   \
-      DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai)                                   \
-      DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai)                                           \
+      unsigned o0t, o1t, o2t, o3t;                                                                                       \
+      DP_CELL(3, vD.z, vaD.z, vI.w, vaI.w, vB.z, vA.z, o3b, o3a, o3d, o3ad, o3i, o3ai, o3t)                              \
+      DP_CELL(2, vD.y, vaD.y, vI.z, vaI.z, vB.y, vA.y, o2b, o2a, o2d, o2ad, o2i, o2ai, o2t)                              \
+      DP_CELL(1, vD.x, vaD.x, vI.y, vaI.y, vB.x, vA.x, o1b, o1a, o1d, o1ad, o1i, o1ai, o1t)                              \
+      DP_CELL(0, sD, saD, vI.x, vaI.x, sB, sA, o0b, o0a, o0d, o0ad, o0i, o0ai, o0t)                                      \
       /* cells of the group outside [nlo, nhi] hold junk nobody reads (the halo is rewritten below), except in the */    \
       /* best buffer, which the trim and the maximum look at */                                                          \
       const int r0 = j0 - nlo;                                                                                           \
@@ -152,6 +173,7 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
       k = o1b * k256 + (r0 + 1); lkey = k > lkey ? k : lkey;                                                             \
       k = o0b * k256 + r0; lkey = k > lkey ? k : lkey;                                                                   \
       B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                   \
+      if (TB) *reinterpret_cast<unsigned*>(tbp + (size_t)d * DP_SLOTS + y) = o0t | (o1t << 8) | (o2t << 16) | (o3t << 24); \
     }                                                                                                                    \
     wsync();                                                                                                             \
   }
@@ -161,7 +183,8 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
 // never gives up); optimal: reaching the far corner only counts if the best score is there.
 // Each lane owns a group of four consecutive j (aligned to 4) per step: 128-bit shared loads and
 // stores, four independent cells of instruction-level parallelism.
-MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal) {
+template <bool TB>
+MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal, bool want_ops) {
   // Every per-diagonal quantity (band limits, best score, finish cell) is the same on all lanes.  Passing the
   // inputs through a warp reduction makes that visible to the compiler (CREDUX writes a uniform register), so
   // the per-diagonal bookkeeping is scheduled on the uniform datapath instead of the saturated vector ALU pipe.
@@ -176,6 +199,8 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;   // re-derived here so accesses compile to LDS/STS
 #endif
   const int lane = lane_id();
+  unsigned char* const tbp = TB ? E.T.tb : nullptr;
+  if (TB && lane == 0) tbp[0] = 2;                    // cell (0,0): diagonal state
   int* nD = sm; int* naD = sm + DP_SLOTS;            // value / aux handed to cell (i, j+1), stored at j
   int* nI = sm + 2 * DP_SLOTS; int* naI = sm + 3 * DP_SLOTS;   // handed to cell (i+1, j), stored at j
   int* bBase = sm + 4 * DP_SLOTS;                    // best state by diagonal parity: value at +0/+DP_SLOTS, aux at +2/+3*DP_SLOTS
@@ -296,7 +321,101 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     E.acc_cells += cells; E.acc_calls += 1ull;
     if (maxw > E.acc_maxw) E.acc_maxw = maxw;
   }
+  o.n_ops = 0;
+  if (TB && want_ops) {
+    // walk back from the finish cell; the columns land in E.T.rev, last column first
+    wsync();
+    int n = 0;
+    if (lane == 0) {
+      unsigned char* rev = E.T.rev;
+      int dd = FinD, jj = FinJ;
+      int s = dd > 0 ? (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u) : 2;
+      while (dd > 0 && n < TB_DIAGS) {
+        if (s == 2) {
+          rev[n++] = 0; dd -= 2; jj -= 1;
+          if (dd > 0) s = (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u);
+        } else if (s == 0) {
+          rev[n++] = 2; dd -= 1; jj -= 1;
+          const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
+          s = (pc & 4u) ? 0 : (int)(pc & 3u);
+        } else {
+          rev[n++] = 1; dd -= 1;
+          const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
+          s = (pc & 8u) ? 1 : (int)(pc & 3u);
+        }
+      }
+      if (dd != 0) E.T.bad = 1;
+    }
+    o.n_ops = wbcast_i32(n, 0);
+    wsync();
+  }
   return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// token lists of the alignments (delta mode, first lane only)
+// ------------------------------------------------------------------------------------------
+MFSC_DEV int tok_alloc(const ExtCtx& E, int n) {
+  if (E.T.top + 2 + n > TB_ARENA_INTS) { E.T.bad = 1; return -1; }
+  const int c = E.T.top;
+  E.T.top += 2 + n;
+  E.T.arena[c] = -1; E.T.arena[c + 1] = n;
+  return c;
+}
+MFSC_DEV int tok_run(const ExtCtx& E, int len) {
+  const int c = tok_alloc(E, 1);
+  if (c >= 0) E.T.arena[c + 2] = len;
+  return c;
+}
+// chunk from the columns of the last traceback (E.T.rev holds them last column first)
+MFSC_DEV int tok_from_rev(const ExtCtx& E, int n) {
+  const unsigned char* rev = E.T.rev;
+  int cnt = 0, run = 0;
+  for (int k = n - 1; k >= 0; k--) { if (rev[k] == 0) run++; else { if (run) cnt++; cnt++; run = 0; } }
+  if (run) cnt++;
+  if (cnt == 0) return -1;
+  const int c = tok_alloc(E, cnt);
+  if (c < 0) return -1;
+  int* t = E.T.arena + c + 2;
+  int w = 0; run = 0;
+  for (int k = n - 1; k >= 0; k--) { if (rev[k] == 0) run++; else { if (run) t[w++] = run; t[w++] = -(int)rev[k]; run = 0; } }
+  if (run) t[w++] = run;
+  return c;
+}
+MFSC_DEV void tok_drop_last_column(const ExtCtx& E, int ci) {      // the DP re-aligns the alignment's last column
+  const int t = E.R.tail[ci];
+  if (t < 0) { E.T.bad = 1; return; }
+  int* last = E.T.arena + t + 2 + E.T.arena[t + 1] - 1;
+  if (*last >= 1) *last -= 1; else E.T.bad = 1;
+}
+MFSC_DEV void tok_drop_first_column(const ExtCtx& E, int ci) {
+  const int h = E.R.head[ci];
+  if (h < 0) { E.T.bad = 1; return; }
+  if (E.T.arena[h + 2] >= 1) E.T.arena[h + 2] -= 1; else E.T.bad = 1;
+}
+MFSC_DEV void tok_append(const ExtCtx& E, int ci, int chunk) {
+  if (chunk < 0) return;
+  const int t = E.R.tail[ci];
+  if (t < 0) { E.R.head[ci] = chunk; E.R.tail[ci] = chunk; return; }
+  E.T.arena[t] = chunk; E.R.tail[ci] = chunk;
+}
+MFSC_DEV void tok_prepend(const ExtCtx& E, int ci, int chunk) {
+  if (chunk < 0) return;
+  E.T.arena[chunk] = E.R.head[ci]; E.R.head[ci] = chunk;
+  if (E.R.tail[ci] < 0) E.R.tail[ci] = chunk;
+}
+// delta values of alignment ci: walk the chunks; returns the count, writes when out != nullptr
+MFSC_DEV int tok_deltas(const ExtCtx& E, int ci, int* out) {
+  int n = 0, run = 0;
+  for (int c = E.R.head[ci]; c >= 0; c = E.T.arena[c]) {
+    const int m = E.T.arena[c + 1];
+    for (int k = 0; k < m; k++) {
+      const int t = E.T.arena[c + 2 + k];
+      if (t >= 0) run += t;
+      else { if (out) out[n] = (t == -1) ? (run + 1) : -(run + 1); n++; run = 0; }
+    }
+  }
+  return n;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -308,47 +427,55 @@ MFSC_DEV int c_s1(const ExtCtx& E, int c, int t) { return (int)(E.cm_s1[E.pc_fir
 MFSC_DEV int c_s2(const ExtCtx& E, int c, int t) { return E.cm_s2[E.pc_first[E.ord[c]] + t] + 1; }
 MFSC_DEV int c_len(const ExtCtx& E, int c, int t) { return E.cm_len[E.pc_first[E.ord[c]] + t]; }
 
+template <bool TB>
 MFSC_DEV bool ext_forward(ExtCtx& E, int ci, int tA, int tB, bool forced, bool optimal) {
   const int eA = E.R.eA[ci], eB = E.R.eB[ci], dir = E.R.dir[ci];
   bool overflow = false;
   if (tA - eA + 1 > DP_MAX_ALN) { tA = eA + DP_MAX_ALN - 1; overflow = true; optimal = true; }
   if (tB - eB + 1 > DP_MAX_ALN) { tB = eB + DP_MAX_ALN - 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal);
+  DpOut o = dp_engine<TB>(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal, true);
   // the DP re-aligns the alignment's last column
   wsync();
   if (E.lane == 0) {
     E.R.cols[ci] += o.cols - 1; E.R.errs[ci] += o.errs;
     E.R.eA[ci] = eA + o.fi - 1; E.R.eB[ci] = eB + o.fj - 1;
+    if (TB) { tok_drop_last_column(E, ci); tok_append(E, ci, tok_from_rev(E, o.n_ops)); }
   }
   wsync();
   return o.reached && !overflow;
 }
 
+template <bool TB>
 MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
   const int sA = E.R.sA[ci], sB = E.R.sB[ci], dir = E.R.dir[ci];
   int tA, tB; bool optimal = false, overflow = false;
   if (ti >= 0) { tA = E.R.eA[ti]; tB = E.R.eB[ti]; } else { tA = 1; tB = 1; optimal = true; }
   if (sA - tA + 1 > DP_MAX_ALN) { tA = sA - DP_MAX_ALN + 1; overflow = true; optimal = true; }
   if (sB - tB + 1 > DP_MAX_ALN) { tB = sB - DP_MAX_ALN + 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal);
+  DpOut o = dp_engine<TB>(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal, false);
   bool reached = o.reached;
   if (overflow || ti < 0) reached = false;
   if (reached) {
-    ext_forward(E, ti, sA, sB, true, false);
+    ext_forward<TB>(E, ti, sA, sB, true, false);
     // the target now ends on this alignment's first column; append the rest and drop this alignment
     if (E.lane == 0) {
       E.R.cols[ti] += E.R.cols[ci] - 1; E.R.errs[ti] += E.R.errs[ci];
       E.R.eA[ti] = E.R.eA[ci]; E.R.eB[ti] = E.R.eB[ci];
+      if (TB) {
+        tok_drop_first_column(E, ci);
+        if (E.R.tail[ti] >= 0 && E.R.head[ci] >= 0) { E.T.arena[E.R.tail[ti]] = E.R.head[ci]; E.R.tail[ti] = E.R.tail[ci]; } else E.T.bad = 1;
+      }
     }
     wsync();
     E.al1--;
   } else {
     const int nsA = sA - o.fi + 1, nsB = sB - o.fj + 1;
-    DpOut o2 = dp_engine(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false);
+    DpOut o2 = dp_engine<TB>(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false, true);
     wsync();
     if (E.lane == 0) {
       E.R.cols[ci] += o2.cols - 1; E.R.errs[ci] += o2.errs;
       E.R.sA[ci] = nsA; E.R.sB[ci] = nsB;
+      if (TB) { tok_drop_first_column(E, ci); tok_prepend(E, ci, tok_from_rev(E, o2.n_ops)); }
     }
     wsync();
   }
@@ -405,6 +532,7 @@ MFSC_DEV int ext_reverse_target(const ExtCtx& E, int cur) {
 }
 
 // Walk the clusters of one (record, read) group in order; returns nothing, alignments are rows [al0, al1)
+template <bool TB>
 MFSC_DEV void ext_clusters(ExtCtx& E) {
   bool target_reached = false;
   int tA = 0, tB = 0;
@@ -424,7 +552,10 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
       if (target_reached) {
         if (E.R.eA[curA] != ms1 || E.R.eB[curA] != ms2) continue;   // walk to the match the DP landed on
         wsync();
-        if (E.lane == 0) { E.R.eA[curA] += mlen - 1; E.R.eB[curA] += mlen - 1; E.R.cols[curA] += mlen - 1; }
+        if (E.lane == 0) {
+          E.R.eA[curA] += mlen - 1; E.R.eB[curA] += mlen - 1; E.R.cols[curA] += mlen - 1;
+          if (TB && mlen > 1) tok_append(E, curA, tok_run(E, mlen - 1));
+        }
         wsync();
       } else {
         curA = E.al1++;
@@ -433,18 +564,19 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
           E.R.ref[curA] = E.ref_id; E.R.qry[curA] = E.qry_id; E.R.dir[curA] = dir;
           E.R.sA[curA] = ms1; E.R.sB[curA] = ms2; E.R.eA[curA] = ms1 + mlen - 1; E.R.eB[curA] = ms2 + mlen - 1;
           E.R.cols[curA] = mlen; E.R.errs[curA] = 0;
+          if (TB) { const int c = tok_run(E, mlen); E.R.head[curA] = c; E.R.tail[curA] = c; }
         }
         wsync();
         const int ti = ext_reverse_target(E, curA);
-        if (ext_backward(E, curA, ti)) curA = ti;
+        if (ext_backward<TB>(E, curA, ti)) curA = ti;
       }
       if (mi < nm - 1) {
         tA = c_s1(E, cur, mi + 1); tB = c_s2(E, cur, mi + 1);
-        target_reached = ext_forward(E, curA, tA, tB, false, false);
+        target_reached = ext_forward<TB>(E, curA, tA, tB, false, false);
       } else {
         tA = E.A.n; tB = E.B[0].n;
         targetC = ext_forward_target(E, cur, tA, tB);
-        target_reached = ext_forward(E, curA, tA, tB, false, targetC < 0);
+        target_reached = ext_forward<TB>(E, curA, tA, tB, false, targetC < 0);
       }
     }
     if (targetC < 0) target_reached = false;
@@ -470,8 +602,11 @@ static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #ifndef MFSC_EXT_MINBLOCKS
 #define MFSC_EXT_MINBLOCKS 6
 #endif
+struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; };
+
+template <bool TB>
 MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
-                                                   unsigned* ticket) {
+                                                   unsigned* ticket, TbPool pool, DeltaOut DO) {
 #ifdef MFSC_EMU
   int* sm = emu_dp_smem;
 #else
@@ -531,6 +666,13 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
     E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0;
+    E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.top = 0; E.T.bad = 0;
+    if (TB) {
+      const long long wg = warp_global();
+      E.T.tb = pool.tb + (size_t)wg * TB_DIAGS * DP_SLOTS;
+      E.T.rev = pool.rev + (size_t)wg * TB_DIAGS;
+      E.T.arena = pool.arena + (size_t)wg * TB_ARENA_INTS;
+    }
     E.B[0].base = QS.start[2 * q]; E.B[0].n = QS.len[2 * q];
     E.B[1].base = QS.start[2 * q + 1]; E.B[1].n = QS.len[2 * q + 1];
     E.pc_rc0 = b1; E.pc_first = I.pc_first; E.pc_n = I.pc_n; E.fused = I.fused;
@@ -545,7 +687,7 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
       E.ord = ord + g0; E.nC = g1 - g0;
       E.A.base = RS.start[rec]; E.A.n = RS.len[rec]; E.a_ostart = I.r_ostart[rec]; E.ref_id = rec;
       E.al0 = row0 + rows; E.al1 = E.al0;
-      ext_clusters(E);
+      ext_clusters<TB>(E);
       rows = E.al1 - row0;
       g0 = g1;
     }
@@ -556,6 +698,20 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
       if (R.dir[row0 + x]) { R.sB[row0 + x] = qlen - R.sB[row0 + x] + 1; R.eB[row0 + x] = qlen - R.eB[row0 + x] + 1; }
     }
     if (lane == 0) R.n_rows[q] = rows;
+    if (TB) {
+      // delta values of the read's alignments go to the batch-wide buffer
+      wsync();
+      if (lane == 0) {
+        for (int x = 0; x < rows; x++) {
+          const int r = row0 + x;
+          const int n = tok_deltas(E, r, nullptr);
+          const long long off = (long long)atomic_add_u64(DO.used, (unsigned long long)n);
+          if (E.T.bad || off + n > DO.cap) { R.dl_begin[r] = -1; R.dl_end[r] = -1; atomic_add_u32(DO.n_bad, 1u); }
+          else { tok_deltas(E, r, DO.buf + off); R.dl_begin[r] = (int)off; R.dl_end[r] = (int)(off + n); }
+        }
+      }
+      wsync();
+    }
     w_cells += E.acc_cells; w_calls += E.acc_calls; if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
   }
   if (lane == 0 && w_calls) {
@@ -574,6 +730,7 @@ MFSC_KERNEL k_compact_rows(RowsOut S, const int* seg, const int* row_off, int n_
       D.ref[dst + x] = S.ref[src + x]; D.qry[dst + x] = S.qry[src + x]; D.dir[dst + x] = S.dir[src + x];
       D.sA[dst + x] = S.sA[src + x]; D.eA[dst + x] = S.eA[src + x]; D.sB[dst + x] = S.sB[src + x]; D.eB[dst + x] = S.eB[src + x];
       D.errs[dst + x] = S.errs[src + x]; D.cols[dst + x] = S.cols[src + x];
+      if (S.dl_begin) { D.dl_begin[dst + x] = S.dl_begin[src + x]; D.dl_end[dst + x] = S.dl_end[src + x]; }
     }
   }
 }

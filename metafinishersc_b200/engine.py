@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import KEEP_CLUSTERS, KEEP_MEMS, STOP_CLUSTERS, STOP_SEEDS, check, make_params, ptr  # noqa: F401
+from ._lib import KEEP_CLUSTERS, KEEP_MEMS, STOP_CLUSTERS, STOP_SEEDS, WANT_DELTAS, check, make_params, ptr  # noqa: F401
 
 
 def _as_buf(seqs):
@@ -21,7 +21,8 @@ def _as_buf(seqs):
 
 class Rows:
     """Alignment rows of one batch in delta order, structure of arrays (int32)."""
-    __slots__ = ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols", "stats", "ms", "mems", "clusters")
+    __slots__ = ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols", "stats", "ms", "mems", "clusters",
+                 "delta_begin", "delta_end", "deltas")
 
     def __len__(self):
         return len(self.s1)
@@ -125,6 +126,11 @@ class Engine:
                            launches=int(st[5]), seed_bytes=int(st[6]), h2d_bytes=int(st[7]), d2h_bytes=int(st[8]))
             r.ms = dict(upload=ms[0], seeds=ms[1], sort=ms[2], cluster=ms[3], extend=ms[4], download=ms[5], total=ms[6])
             r.mems = r.clusters = None
+            r.delta_begin = r.delta_end = r.deltas = None
+            if flags & WANT_DELTAS:
+                r.delta_begin, r.delta_end = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+                r.deltas = np.zeros(L.mfsc_result_count(h, 4), dtype=np.int32)
+                check(L, L.mfsc_result_deltas(h, ptr(r.delta_begin), ptr(r.delta_end), ptr(r.deltas)))
             if flags & KEEP_MEMS:
                 m = L.mfsc_result_count(h, 1)
                 q, st_, s2, ln = [np.zeros(m, dtype=np.int32) for _ in range(4)]
@@ -159,6 +165,7 @@ class Engine:
             z = np.zeros(0, dtype=np.int32)
             r.ref_id = r.qry_id = r.s1 = r.e1 = r.s2 = r.e2 = r.errors = r.cols = z
             r.stats, r.ms, r.mems, r.clusters = {}, {}, None, None
+            r.delta_begin = r.delta_end = r.deltas = None
             return r
         h = ctypes.c_void_p()
         check(self.L, self.L.mfsc_align_batch(index.h, ptr(buf), ptr(off), len(off) - 1, ctypes.byref(params), flags, ctypes.byref(h)))
@@ -192,4 +199,6 @@ class Engine:
         ql = np.ascontiguousarray(qry_len, dtype=np.int32)
         check(self.L, self.L.mfsc_write_delta(path.encode(), ref_path.encode(), qry_path.encode(), len(rows), ptr(rows.ref_id),
                                               ptr(rows.qry_id), ptr(rows.s1), ptr(rows.e1), ptr(rows.s2), ptr(rows.e2),
-                                              ptr(rows.errors), ptr(rows.cols), rn, ptr(rl), len(ref_names), qn, ptr(ql), len(qry_names)))
+                                              ptr(rows.errors), ptr(rows.cols), rn, ptr(rl), len(ref_names), qn, ptr(ql), len(qry_names),
+                                              ptr(getattr(rows, "delta_begin", None)), ptr(getattr(rows, "delta_end", None)),
+                                              ptr(getattr(rows, "deltas", None))))

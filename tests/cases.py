@@ -94,4 +94,19 @@ def run_case(E, O, ref, qry, opts):
                    got[first].tolist() if first < len(got) else None, want[first].tolist() if first < len(want) else None))
     if len(r) and r.stats["cells"] != o["stats"]["cells"]:
         bad.append("DP cells differ: %d vs %d" % (r.stats["cells"], o["stats"]["cells"]))
+    # delta mode: same rows, plus the indel offset list of every row bit-exact
+    ix = E.index(ref, P)
+    rd = E.align(ix, qry, P, flags=engine.WANT_DELTAS)
+    ix.free()
+    gotd = np.stack([rd.ref_id, rd.qry_id, (rd.s2 > rd.e2).astype(np.int32), rd.s1, rd.e1, rd.s2, rd.e2, rd.errors, rd.cols],
+                    axis=1).astype(np.int64) if len(rd) else np.zeros((0, 9), dtype=np.int64)
+    if not np.array_equal(gotd, want):
+        bad.append("delta mode changes the rows")
+    else:
+        for i in range(len(rd)):
+            mine = rd.deltas[rd.delta_begin[i]:rd.delta_end[i]]
+            ref_d = o["deltas"][o["rows"][i, 9]:o["rows"][i, 10]]
+            if rd.delta_begin[i] < 0 or not np.array_equal(mine.astype(np.int64), ref_d):
+                bad.append("delta list of row %d differs: %s... vs %s..." % (i, mine[:6].tolist(), ref_d[:6].tolist()))
+                break
     return bad, r, o

@@ -88,10 +88,28 @@ def run_pipeline(engine, oracle, tmp_path):
     o1 = oracle.align(d["contigs"], parts[0][1], band_cap=248)
     text = oracle.coords_text(o1["rows"], cnames, parts[0][0], folder + "LC_filtered.fasta", folder + "SR.part-01.fasta")
     assert open(folder + "SR2LC_filteredAlign01Out").read().split("\n")[1:] == text.split("\n")[1:]
-    # resume path: rows reloaded from the delta file give the same coords text
+    # the delta file is a real MUMmer delta: header, per alignment the oracle's indel offsets, terminating 0
+    dl = open(folder + "SR2LC_filteredAlign01.delta").read().split("\n")
+    assert dl[1] == "NUCMER" and dl[2].startswith(">Segkk")
+    k = 3
+    for row in o1["rows"]:
+        if dl[k].startswith(">"):
+            k += 1
+        hdr = dl[k].split()
+        assert [int(x) for x in hdr[:5]] == [int(row[3]), int(row[4]), int(row[5]), int(row[6]), int(row[7])] and hdr[6] == "0"
+        want_d = [str(int(x)) for x in o1["deltas"][row[9]:row[10]]] + ["0"]
+        assert dl[k + 1:k + 1 + len(want_d)] == want_d
+        k += 1 + len(want_d)
+    # resume path: rows reloaded from the delta file give the same coords text (both delta forms)
     alignerRobot.clear_caches()
     alignerRobot.showCoorMummer(False, "", folder, "SR2LC_filteredAlign01", "")
     assert open(folder + "SR2LC_filteredAlign01Out").read().split("\n")[5:] == text.split("\n")[5:]
+    alignerRobot.fullDelta = False
+    alignerRobot.useMummerAlign("", folder, "hdronly", "LC_filtered.fasta", "SR.part-01.fasta")
+    alignerRobot.fullDelta = True
+    alignerRobot.clear_caches()
+    alignerRobot.showCoorMummer(False, "", folder, "hdronly", "")
+    assert open(folder + "hdronlyOut").read().split("\n")[5:] == text.split("\n")[5:]
     # A-Splitter abundance on the same rows
     fasta.write_fasta(folder + "improved3.fasta", cnames, d["contigs"])
     fasta.write_fasta(folder + "raw_reads.fasta", datagen.names("Segkk", len(reads)), reads)
