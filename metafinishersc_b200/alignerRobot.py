@@ -112,7 +112,13 @@ def _run_nucmer(prefix, ref_path, qry_path, params):
     ix, rnames, rlens = _get_index(E, ref_path, params)
     qnames, qbuf, qoff = fasta.read_fasta_arrays(qry_path)
     qnames = [n.split()[0] if n.split() else n for n in qnames]
-    rows = E.align(ix, (qbuf, qoff), params, flags=_engine_mod.WANT_DELTAS if fullDelta else 0)
+    try:
+        rows = E.align(ix, (qbuf, qoff), params, flags=_engine_mod.WANT_DELTAS if fullDelta else 0)
+    except _engine_mod._lib.MfscError as err:
+        if not fullDelta or "delta lists" not in str(err):
+            raise
+        print("note: delta lists did not fit for %s, writing alignment headers only (%s)" % (qry_path, err))
+        rows = E.align(ix, (qbuf, qoff), params)
     rs = RowSet(rows, rnames, rlens, qnames, np.diff(qoff).tolist(), ref_path, qry_path)
     while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX:
         _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)))

@@ -607,7 +607,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
 #endif
       // persistent grid: as many blocks as are resident at once, reads handed out by ticket
       unsigned* ext_ticket = (unsigned*)(d_stats + 3);
-      TbPool pool; pool.tb = nullptr; pool.rev = nullptr; pool.arena = nullptr;
+      TbPool pool; pool.tb = nullptr; pool.rev = nullptr; pool.arena = nullptr; pool.arena_ints = 0;
       DeltaOut DO; DO.buf = nullptr; DO.used = nullptr; DO.cap = 0; DO.n_bad = nullptr;
       if (!want_deltas) {
         unsigned ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 4);
@@ -635,7 +635,12 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         }
 #endif
         const size_t n_warps = (size_t)tb_grid * (tb_block / MFSC_LANES);
-        DA(unsigned char, p_tb, n_warps * TB_DIAGS * DP_SLOTS); DA(unsigned char, p_rev, n_warps * TB_DIAGS); DA(int, p_arena, n_warps * TB_ARENA_INTS);
+        // token arena per warp: a read of L bases has at most ~2L columns per alignment, two tokens per indel
+        int max_qlen = 0;
+        for (int r = 0; r < n_reads; r++) max_qlen = std::max(max_qlen, rd->q.h_len[2 * r]);
+        const int arena_ints = std::max(1 << 16, 4 * max_qlen + 4096);
+        DA(unsigned char, p_tb, n_warps * TB_DIAGS * DP_SLOTS); DA(unsigned char, p_rev, n_warps * TB_DIAGS); DA(int, p_arena, n_warps * (size_t)arena_ints);
+        pool.arena_ints = arena_ints;
         DA(int, x_head, M); DA(int, x_tail, M); DA(int, x_dlb, M); DA(int, x_dle, M);
         const long long dcap = rd->q.n_bases / 2 + (1 << 20);
         DA(int, d_delta, dcap); DA(unsigned long long, d_used, 2);

@@ -60,11 +60,10 @@ struct RowsOut {
 // after each DP that contributes columns to an alignment, and keeps every alignment as a linked list of token
 // chunks (run of diagonal columns >= 0, -1 = column consuming A only, -2 = column consuming B only).
 #define TB_DIAGS (2 * DP_MAX_ALN + 8)
-#define TB_ARENA_INTS (1 << 16)
 struct TbCtx {
   unsigned char* tb;    // [TB_DIAGS * DP_SLOTS] codes of the current DP, row d, column j & DP_SMASK
   unsigned char* rev;   // [TB_DIAGS] columns of the last traceback, last column first (0 diagonal, 1 A only, 2 B only)
-  int* arena; int top; int bad;
+  int* arena; int cap; int top; int bad;      // token arena of the read being extended (cap ints)
 };
 struct DeltaOut { int* buf; unsigned long long* used; long long cap; unsigned* n_bad; };
 
@@ -356,7 +355,7 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
 // token lists of the alignments (delta mode, first lane only)
 // ------------------------------------------------------------------------------------------
 MFSC_DEV int tok_alloc(const ExtCtx& E, int n) {
-  if (E.T.top + 2 + n > TB_ARENA_INTS) { E.T.bad = 1; return -1; }
+  if (E.T.top + 2 + n > E.T.cap) { E.T.bad = 1; return -1; }
   const int c = E.T.top;
   E.T.top += 2 + n;
   E.T.arena[c] = -1; E.T.arena[c + 1] = n;
@@ -602,7 +601,7 @@ static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #ifndef MFSC_EXT_MINBLOCKS
 #define MFSC_EXT_MINBLOCKS 6
 #endif
-struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; };
+struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; int arena_ints; };
 
 template <bool TB>
 MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
@@ -666,12 +665,12 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
     E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0;
-    E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.top = 0; E.T.bad = 0;
+    E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.cap = 0; E.T.top = 0; E.T.bad = 0;
     if (TB) {
       const long long wg = warp_global();
       E.T.tb = pool.tb + (size_t)wg * TB_DIAGS * DP_SLOTS;
       E.T.rev = pool.rev + (size_t)wg * TB_DIAGS;
-      E.T.arena = pool.arena + (size_t)wg * TB_ARENA_INTS;
+      E.T.arena = pool.arena + (size_t)wg * pool.arena_ints; E.T.cap = pool.arena_ints;
     }
     E.B[0].base = QS.start[2 * q]; E.B[0].n = QS.len[2 * q];
     E.B[1].base = QS.start[2 * q + 1]; E.B[1].n = QS.len[2 * q + 1];
