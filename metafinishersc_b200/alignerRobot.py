@@ -99,9 +99,9 @@ def _get_index(E, ref_path, params):
     return _INDEX_CACHE[key]
 
 
-def _run_nucmer(prefix, ref_path, qry_path, params):
+def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
     """One nucmer job: rows cached under `<prefix>.delta` and the delta file written."""
-    E = get_engine()
+    E = E or get_engine()
     delta = prefix + ".delta"
     if not (os.path.exists(ref_path) and os.path.exists(qry_path)):
         print("ERROR: Could not find input file(s) %s %s" % (ref_path, qry_path))   # nucmer's failure is ignored upstream too
@@ -109,7 +109,7 @@ def _run_nucmer(prefix, ref_path, qry_path, params):
         if os.path.exists(delta):
             os.remove(delta)
         return None
-    ix, rnames, rlens = _get_index(E, ref_path, params)
+    ix, rnames, rlens = index_entry if index_entry is not None else _get_index(E, ref_path, params)
     qnames, qbuf, qoff = fasta.read_fasta_arrays(qry_path)
     qnames = [n.split()[0] if n.split() else n for n in qnames]
     try:
@@ -222,6 +222,9 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
     The Pool / MPI fan-out becomes a loop over the jobs on the GPU (nProc is advisory); jobs that share a
     reference share its index.  globalLarge reproduces the row order of the 10x10 tiling."""
     if not houseKeeper.globalLarge:
+        if houseKeeper.globalGPUs > 1 and len(workerList) > 1:
+            _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, houseKeeper.globalGPUs)
+            return
         for outputName, referenceName, queryName, specialName in workerList:
             useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
         return
@@ -249,6 +252,51 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
         for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
             setattr(sub, f, np.ascontiguousarray(getattr(r, f)[sel]))
         get_engine().write_coords(out, sub, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=False)
+
+
+def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus):
+    """The reference's Pool(nProc) fan-out (alignerRobot.py:154-166) over the GPUs of one box: one host thread per
+    GPU (the C library keeps one device context and stream per thread), jobs dealt round-robin, every thread builds
+    the index of the references it meets on its own device.  Output files are the same as in the serial loop."""
+    import threading
+    main = get_engine()
+    params = _params(refinedVersion)
+    errors = []
+
+    def work(dev):
+        try:
+            E = _engine_mod.Engine(main.L)
+            E.set_device(dev)
+            local = {}                       # reference path -> index entry on this device
+            for k in range(dev, len(workerList), n_gpus):
+                outputName, referenceName, queryName, specialName = workerList[k]
+                ref_path = folderName + referenceName
+                qry_path = queryName if specialForRaw else folderName + queryName
+                entry = None
+                if os.path.exists(ref_path):
+                    if ref_path not in local:
+                        names, buf, off = fasta.read_fasta_arrays(ref_path)
+                        names = [n.split()[0] if n.split() else n for n in names]
+                        local[ref_path] = (E.index((buf, off), params), names, np.diff(off).tolist())
+                    entry = local[ref_path]
+                rs = _run_nucmer(folderName + outputName, ref_path, qry_path, params, E=E, index_entry=entry)
+                out = folderName + (specialName if specialForRaw else outputName + "Out")
+                if rs is None:
+                    open(out, "w").close()
+                else:
+                    E.write_coords(out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=True)
+            for ix, _, _ in local.values():
+                ix.free()
+        except Exception as e:       # surfaced in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in range(n_gpus)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
 
 
 def transformCoor(dataList):

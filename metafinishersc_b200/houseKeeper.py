@@ -7,3 +7,4 @@ globalLarge = False           # 10x10 reference x query tiling in the reference;
 globalRelaxThres = False
 globalRunMPI = False          # the MPI fan-out is replaced by in-process dispatch
 globalParallelFileNum = 20    # read parts per reads-vs-contigs alignment
+globalGPUs = 1                # GPUs of this box the batch calls may use (one host thread per GPU); not in the reference

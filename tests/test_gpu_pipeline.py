@@ -106,3 +106,23 @@ def test_cfg5_scale_index(gpu_engine):
     assert len(best) == n_reads
     ok = sum(1 for q, (ln, c, s1) in best.items() if c == starts[q][0] and abs(s1 - 1 - starts[q][1]) <= 50 and ln > 9000)
     assert ok == n_reads
+
+
+def test_batch_over_two_gpus(gpu_engine, oracle, tmp_path):
+    """In-process fan-out of the 20 read parts over two GPUs (one host thread per GPU): same files as the serial loop."""
+    from metafinishersc_b200 import alignerRobot, houseKeeper
+    if gpu_engine.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    alignerRobot.set_engine(gpu_engine)
+    folder, d, reads = test_host_pipeline.make_folder(tmp_path, n_reads=200)
+    serial = alignerRobot.largeRvsQAlign(folder, 20, "", "LC_filtered", "SR", "serial")
+    houseKeeper.globalGPUs = 2
+    try:
+        par = alignerRobot.largeRvsQAlign(folder, 20, "", "LC_filtered", "SR", "par")
+    finally:
+        houseKeeper.globalGPUs = 1
+    assert par == serial and len(par) > 0
+    for i in range(1, 21):
+        idx = alignerRobot.zeropadding(i)
+        assert open(folder + "par" + idx + ".delta").read().split("\n")[1:] == open(folder + "serial" + idx + ".delta").read().split("\n")[1:]
+    alignerRobot.set_engine(None)

@@ -159,3 +159,21 @@ def test_large_mode_order(emu_engine, oracle, tmp_path):
     want = oracle.coords_rows(o["rows"], ["Segkk0", "Segkk1"], datagen.names("Segkk", len(reads)))
     assert sorted(map(tuple, rows)) == sorted(map(tuple, want))
     alignerRobot.set_engine(None)
+
+
+def test_batch_over_two_devices_emu(emu_engine, oracle, tmp_path):
+    """The in-process fan-out over GPUs (one host thread per device) writes the same files as the serial loop."""
+    alignerRobot.set_engine(emu_engine)
+    folder, d, reads = make_folder(tmp_path, n_reads=80)
+    serial = alignerRobot.largeRvsQAlign(folder, 20, "", "LC_filtered", "SR", "serial")
+    houseKeeper.globalGPUs = 2
+    try:
+        par = alignerRobot.largeRvsQAlign(folder, 20, "", "LC_filtered", "SR", "par")
+    finally:
+        houseKeeper.globalGPUs = 1
+    assert par == serial and len(par) > 0
+    for i in range(1, 21):
+        idx = alignerRobot.zeropadding(i)
+        assert open(folder + "par" + idx + "Out").read().split("\n")[1:] == open(folder + "serial" + idx + "Out").read().split("\n")[1:]
+        assert open(folder + "par" + idx + ".delta").read().split("\n")[1:] == open(folder + "serial" + idx + ".delta").read().split("\n")[1:]
+    alignerRobot.set_engine(None)
