@@ -127,8 +127,10 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     contigs, reads = make_workload(0, args.reads, args.genome)
-    # pilots size the per-step sample (~ args.ref_step_seconds of CPU work on all threads)
-    n_sample = size_sample(contigs, reads, threads, args.ref_step_seconds)
+    # pilots size the per-step sample: ~ args.ref_step_seconds of CPU work on all threads, less when many steps are asked
+    # for, so that the whole run stays within a few minutes
+    step_s = min(args.ref_step_seconds, 150.0 / max(1, args.steps + args.warmup))
+    n_sample = size_sample(contigs, reads, threads, step_s)
     reads = reads[:n_sample]
     for _ in range(args.warmup):
         oracle_rate(contigs, reads[:threads], threads)
