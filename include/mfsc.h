@@ -139,6 +139,18 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
                      const char* qry_names, const int32_t* qry_len, int32_t n_qry,
                      const int64_t* d_begin, const int64_t* d_end, const int32_t* deltas /* all three NULL: headers only */);
 
+/* FASTA ingest and part writing on the host (the O(bases) work either side of the aligner: fasta-splitter.pl:135-183,
+ * IORobot.py:8-30).  mfsc_fasta_parse: data[n] = file bytes; bases_out[<= n] receives the concatenated sequence
+ * characters, off_out[max_rec+1] the record offsets, name_span_out[2*max_rec] the [begin, end) of every header text
+ * (after '>') inside data.  Blank lines are skipped, '\r' is stripped, sequence lines before the first header are
+ * ignored.  Returns MFSC_ERR_ARG when there are more than max_rec records (n_rec_out then holds the count needed).
+ * mfsc_fasta_write: records [rec_begin, rec_end) as ">name\n" + sequence wrapped at line_len columns (0: one line). */
+int mfsc_fasta_parse(const uint8_t* data, int64_t n, uint8_t* bases_out, int64_t* off_out, int64_t* name_span_out,
+                     int32_t max_rec, int32_t* n_rec_out);
+int mfsc_fasta_count(const uint8_t* data, int64_t n, int32_t* n_rec_out);
+int mfsc_fasta_write(const char* path, const char* names, const int64_t* name_off, const uint8_t* bases, const int64_t* off,
+                     int32_t rec_begin, int32_t rec_end, int32_t line_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_dev
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_reads_upload", "mfsc_reads_free",
            "mfsc_align_reads", "mfsc_align_batch", "mfsc_result_count", "mfsc_result_rows", "mfsc_result_mems",
            "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_write_coords",
-           "mfsc_write_delta"]
+           "mfsc_write_delta", "mfsc_fasta_parse", "mfsc_fasta_count", "mfsc_fasta_write"]
 
 
 class MfscError(RuntimeError):
@@ -80,6 +80,9 @@ def bind(path):
         [ctypes.c_char_p, c_i32, ctypes.c_char_p, c_i32, c_i32]
     L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_vp, c_i32, ctypes.c_char_p, c_vp, c_i32, c_vp, c_vp, c_vp]
+    L.mfsc_fasta_parse.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32)]
+    L.mfsc_fasta_count.argtypes = [c_vp, c_i64, ctypes.POINTER(c_i32)]
+    L.mfsc_fasta_write.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]
     return L
 
 

@@ -883,4 +883,68 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
   return MFSC_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// FASTA ingest / part writing (host)
+// ------------------------------------------------------------------------------------------
+int mfsc_fasta_count(const uint8_t* data, int64_t n, int32_t* n_rec_out) {
+  if (!data || n < 0 || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_count: bad arguments");
+  int32_t c = 0;
+  int64_t i = 0;
+  while (i < n) {
+    if (data[i] == '>') c++;
+    const void* e = memchr(data + i, '\n', (size_t)(n - i));
+    if (!e) break;
+    i = (const uint8_t*)e - data + 1;
+  }
+  *n_rec_out = c;
+  return MFSC_OK;
+}
+
+int mfsc_fasta_parse(const uint8_t* data, int64_t n, uint8_t* bases_out, int64_t* off_out, int64_t* name_span_out, int32_t max_rec,
+                     int32_t* n_rec_out) {
+  if (!data || n < 0 || !bases_out || !off_out || !name_span_out || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: bad arguments");
+  int32_t rec = 0; int64_t w = 0, i = 0;
+  off_out[0] = 0;
+  while (i < n) {
+    const void* nl = memchr(data + i, '\n', (size_t)(n - i));
+    const int64_t e = nl ? (const uint8_t*)nl - data : n;
+    int64_t le = e;
+    while (le > i && (data[le - 1] == '\r')) le--;
+    if (le > i) {
+      if (data[i] == '>') {
+        if (rec >= max_rec) { int32_t c = 0; mfsc_fasta_count(data, n, &c); *n_rec_out = c; return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: more records than max_rec"); }
+        if (rec > 0) off_out[rec] = w;
+        name_span_out[2 * rec] = i + 1; name_span_out[2 * rec + 1] = le;
+        rec++;
+      } else if (rec > 0) {
+        memcpy(bases_out + w, data + i, (size_t)(le - i));
+        w += le - i;
+      }
+    }
+    i = e + 1;
+  }
+  off_out[rec] = w;
+  *n_rec_out = rec;
+  return MFSC_OK;
+}
+
+int mfsc_fasta_write(const char* path, const char* names, const int64_t* name_off, const uint8_t* bases, const int64_t* off, int32_t rec_begin,
+                     int32_t rec_end, int32_t line_len) {
+  if (!path || !names || !name_off || !bases || !off || rec_begin < 0 || rec_end < rec_begin) return fail(MFSC_ERR_ARG, "mfsc_fasta_write: bad arguments");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(MFSC_ERR_IO, std::string("cannot open ") + path);
+  std::vector<char> buf(1 << 20);
+  setvbuf(f, buf.data(), _IOFBF, buf.size());
+  for (int32_t r = rec_begin; r < rec_end; r++) {
+    fputc('>', f);
+    fwrite(names + name_off[r], 1, (size_t)(name_off[r + 1] - name_off[r]), f);
+    fputc('\n', f);
+    const int64_t b = off[r], e = off[r + 1];
+    if (line_len <= 0) { fwrite(bases + b, 1, (size_t)(e - b), f); fputc('\n', f); }
+    else for (int64_t p = b; p < e; p += line_len) { fwrite(bases + p, 1, (size_t)std::min<int64_t>(line_len, e - p), f); fputc('\n', f); }
+  }
+  fclose(f);
+  return MFSC_OK;
+}
+
 }  // extern "C"

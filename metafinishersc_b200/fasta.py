@@ -32,40 +32,23 @@ def read_fasta(path):
 
 
 def read_fasta_arrays(path):
-    """Vectorised ingest for the aligner: -> (names list[str], uint8 bases, int64 offsets[n+1]).
-    Same records as read_fasta (blank lines skipped, sequence lines joined), without per-line Python work."""
-    data = np.fromfile(path, dtype=np.uint8)
-    if data.size == 0:
-        return [], np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
-    nl = np.flatnonzero(data == 10)
-    starts = np.concatenate(([0], nl + 1))
-    ends = np.concatenate((nl, [data.size]))
-    if starts[-1] >= data.size:                       # file ends with a newline
-        starts, ends = starts[:-1], ends[:-1]
-    ends = ends - ((ends > starts) & (data[np.maximum(ends - 1, 0)] == 13))      # strip \r
-    nonempty = ends > starts
-    starts, ends = starts[nonempty], ends[nonempty]
-    is_hdr = data[starts] == 62
-    hdr_idx = np.flatnonzero(is_hdr)
-    if hdr_idx.size == 0:
-        return [], np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
-    raw = data.tobytes()
-    names = [raw[starts[i] + 1:ends[i]].decode() for i in hdr_idx]
-    # sequence lines before the first header are ignored (read_fasta does the same)
-    seq_mask = ~is_hdr
-    seq_mask[:hdr_idx[0]] = False
-    lens = np.where(seq_mask, ends - starts, 0)
-    # record of each line = number of headers seen so far - 1
-    rec_of_line = np.cumsum(is_hdr) - 1
-    off = np.zeros(len(names) + 1, dtype=np.int64)
-    np.add.at(off, rec_of_line[seq_mask] + 1, lens[seq_mask])
-    np.cumsum(off, out=off)
-    # gather the bases: byte-level keep mask from a +1/-1 difference array over line spans
-    diff = np.zeros(data.size + 1, dtype=np.int8)
-    np.add.at(diff, starts[seq_mask], 1)
-    np.add.at(diff, ends[seq_mask], -1)
-    keep = np.cumsum(diff[:-1], dtype=np.int8).astype(bool)
-    return names, np.ascontiguousarray(data[keep]), off
+    """Ingest for the aligner: -> (names list[str], uint8 bases, int64 offsets[n+1]).  Same records as read_fasta
+    (blank lines skipped, sequence lines joined); one pass in C (mfsc_fasta_parse), no per-line Python work."""
+    import ctypes
+    from . import _lib
+    L = _lib.load()
+    size = os.path.getsize(path)
+    data = np.memmap(path, dtype=np.uint8, mode="r") if size > (1 << 24) else np.fromfile(path, dtype=np.uint8)   # big files: parse straight from the page cache
+    n_rec = ctypes.c_int32(0)
+    _lib.check(L, L.mfsc_fasta_count(_lib.ptr(data), data.size, ctypes.byref(n_rec)))
+    n = n_rec.value
+    bases = np.empty(max(int(data.size), 1), dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.int64)
+    spans = np.zeros(2 * max(n, 1), dtype=np.int64)
+    _lib.check(L, L.mfsc_fasta_parse(_lib.ptr(data), data.size, _lib.ptr(bases), _lib.ptr(off), _lib.ptr(spans), n, ctypes.byref(n_rec)))
+    raw = memoryview(data)
+    names = [bytes(raw[spans[2 * i]:spans[2 * i + 1]]).decode() for i in range(n)]
+    return names, bases[:int(off[n])], off
 
 
 def write_fasta(path, names, seqs, line_len=0):
@@ -97,10 +80,13 @@ def obtain_length(path):
 def part_boundaries(names, seqs, n_parts, line_len=60):
     """Record index ranges [(begin, end), ...] of the parts fasta-splitter.pl would write
     (fasta-splitter.pl:160-183, measure=all, unix eol)."""
-    def seq_size(name, s):
-        slen = len(s)
-        return slen + len(name) + 1 + (1 + ((slen + line_len - 1) // line_len if line_len else 1))
-    sizes = [seq_size(n, s) for n, s in zip(names, seqs)]
+    return part_boundaries_len([len(n) for n in names], [len(s) for s in seqs], n_parts, line_len)
+
+
+def part_boundaries_len(name_lens, seq_lens, n_parts, line_len=60):
+    def seq_size(nlen, slen):
+        return slen + nlen + 1 + (1 + ((slen + line_len - 1) // line_len if line_len else 1))
+    sizes = [seq_size(int(n), int(s)) for n, s in zip(name_lens, seq_lens)]
     total = sum(sizes)
     parts, begin = [], 0
     written_total, written_this, part, part_end, opened = 0, 0, 1, int(total / n_parts), False
@@ -124,8 +110,16 @@ def part_boundaries(names, seqs, n_parts, line_len=60):
 def split_fasta(path, n_parts, out_dir=None, line_len=60):
     """Write <base>.part-NN.fasta files; returns their paths.  fasta-splitter.pl writes into
     the CWD and alignerRobot.py:268-269 then copies them into the folder; callers pass
-    out_dir=folder to land them there directly."""
-    names, seqs = read_fasta(path)
+    out_dir=folder to land them there directly.  Parsing and the wrapped part files are done in C
+    (mfsc_fasta_parse / mfsc_fasta_write); the part boundaries follow the Perl script."""
+    from . import _lib
+    L = _lib.load()
+    names, bases, off = read_fasta_arrays(path)
+    enc = [n.encode() for n in names]
+    name_off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(e) for e in enc], out=name_off[1:])
+    blob = b"".join(enc) + b"\0"
     base = os.path.basename(path)
     ext = ""
     for e in (".fasta", ".faa", ".fna", ".fa"):
@@ -135,9 +129,12 @@ def split_fasta(path, n_parts, out_dir=None, line_len=60):
     out_dir = out_dir if out_dir is not None else os.getcwd()
     num_len = len(str(n_parts))
     paths = []
-    for p, (b, e) in enumerate(part_boundaries(names, seqs, n_parts, line_len), start=1):
+    bounds = part_boundaries_len(np.diff(name_off), np.diff(off), n_parts, line_len)
+    bases = np.ascontiguousarray(bases)
+    for p, (b, e) in enumerate(bounds, start=1):
         stem = base if (".part-" in base and base.rsplit(".part-", 1)[1].isdigit()) else base + ".part"
         out = os.path.join(out_dir, "%s-%0*d%s" % (stem, num_len, p, ext))
-        write_fasta(out, names[b:e], seqs[b:e], line_len)
+        _lib.check(L, L.mfsc_fasta_write(out.encode(), blob, _lib.ptr(name_off), _lib.ptr(bases) if bases.size else _lib.ptr(np.zeros(1, np.uint8)),
+                                         _lib.ptr(off), b, e, line_len))
         paths.append(out)
     return paths
