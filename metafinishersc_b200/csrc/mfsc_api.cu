@@ -862,6 +862,8 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
   std::vector<const char*> rn = split_names(ref_names, n_ref), qn = split_names(qry_names, n_qry);
   FILE* f = fopen(path, "w");
   if (!f) return fail(MFSC_ERR_IO, std::string("cannot open ") + path);
+  std::vector<char> iobuf(1 << 20);
+  setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
   fprintf(f, "%s %s\nNUCMER\n", ref_path, qry_path);
   int last_r = -1, last_q = -1;
   for (int64_t i = 0; i < n_rows; i++) {
@@ -872,8 +874,21 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
     if (deltas && d_begin && d_begin[i] >= 0) {
       // a real MUMmer delta record: header, signed distances to the next indel, terminating 0
       fprintf(f, "%d %d %d %d %d %d 0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i]);
-      for (int64_t k = d_begin[i]; k < d_end[i]; k++) fprintf(f, "%d\n", deltas[k]);
-      fprintf(f, "0\n");
+      // tens of millions of short lines: format by hand into a block buffer
+      char blk[1 << 16];
+      size_t w = 0;
+      for (int64_t k = d_begin[i]; k < d_end[i]; k++) {
+        if (w + 16 > sizeof(blk)) { fwrite(blk, 1, w, f); w = 0; }
+        int v = deltas[k];
+        unsigned u = v < 0 ? (unsigned)(-(long long)v) : (unsigned)v;
+        if (v < 0) blk[w++] = '-';
+        char tmp[12]; int n = 0;
+        do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+        while (n) blk[w++] = tmp[--n];
+        blk[w++] = '\n';
+      }
+      blk[w++] = '0'; blk[w++] = '\n';
+      fwrite(blk, 1, w, f);
     } else {
       // header only (the default traceback-free DP produces no indel list); the 7th field carries the column count
       fprintf(f, "%d %d %d %d %d %d %d\n0\n", s1[i], e1[i], s2[i], e2[i], errors[i], errors[i], cols[i]);
