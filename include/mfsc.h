@@ -62,9 +62,10 @@ int mfsc_host_free(void* p);
  * rec_off[n_rec+1]: offsets of the records in bases. */
 int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                      mfsc_index** out);
-/* Replication over several GPUs: every rank creates the index with `build_tables` = 0 except the root,
- * fetches the device buffers and broadcasts them (NCCL via torch.distributed, one call per buffer),
- * then calls mfsc_index_commit.  info: [0] k, [1] stride, [2] text words, [3] buckets+2, [4] positions,
+/* Replication over several GPUs: the root rank builds the index; every other rank creates an empty one of the
+ * same shape (`build_tables` = 0, `p->kmer` and `n_positions` taken from the root's mfsc_index_info, `bases` may be
+ * NULL), then all ranks fetch the device buffers with mfsc_index_buffers and broadcast them (NCCL through
+ * torch.distributed, one call per buffer).  info: [0] k, [1] unused, [2] text words, [3] buckets+2, [4] positions,
  * [5] bytes in HBM, [6] records, [7] bases. */
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                       int32_t build_tables, int64_t n_positions, mfsc_index** out);

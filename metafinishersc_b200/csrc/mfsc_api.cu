@@ -27,8 +27,6 @@ thread_local emu_dim3 emu_threadIdx, emu_blockIdx, emu_blockDim, emu_gridDim;
 // ------------------------------------------------------------------------------------------
 namespace {
 
-struct Timer;
-
 #ifdef MFSC_EMU
 struct Dev {
   cudaStream_t stream = 0;
@@ -48,7 +46,6 @@ static void stamp(Dev&, Stamp& s) { s.t = std::chrono::steady_clock::now(); }
 static double elapsed_ms(Dev&, Stamp& a, Stamp& b) { return std::chrono::duration<double, std::milli>(b.t - a.t).count(); }
 static void stamp_free(Stamp&) {}
 #else
-static bool g_pool_init = false;
 struct Dev {
   cudaStream_t stream = 0;
   long long launches = 0;
@@ -519,6 +516,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     cap = (long long)found + 1024;
   }
   keep(m_qs); keep(m_s1); keep(m_s2); keep(m_len); keep(m_rec);
+  if ((unsigned long long)found >= 0x7fffffffull) { cleanup(); delete res; return fail(MFSC_ERR_ARG, "more than 2^31 matches in one batch: split the reads into smaller batches"); }
   const long long M = found;
   res->n_mems = M;
   res->stats[3] = n_probes; res->stats[4] = M;
