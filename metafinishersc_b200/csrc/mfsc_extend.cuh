@@ -177,6 +177,29 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
     wsync();                                                                                                             \
   }
 
+// Narrow diagonals (at most one cell per lane): the same cell arithmetic without the group-of-four machinery.
+// Lane l owns j = nhi - l.  B0/BJ receive the lane's best-state value (DP_NEG when the lane is idle) and its j.
+#define DP_PASS1(B0, BJ)                                                                                                 \
+  {                                                                                                                      \
+    const bool act1 = lane < w;                                                                                          \
+    const int j1 = act1 ? nhi - lane : nhi;          /* idle lanes shadow the top cell (loads only) */                   \
+    const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;                                                               \
+    const int sD = nD[y1], saD = naD[y1], sI = nI[y], saI = naI[y], sB = cB[y1], sA = cA[y1];                            \
+    const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
+    const unsigned xm = ca1 ^ cb1, ym = xm | ((ca1 | cb1) & 4u);                                                         \
+    wsync();                                                                                                             \
+    if (act1) {                                                                                                          \
+      int ob, oa, od, oad, oi, oai; unsigned ot;                                                                         \
+      DP_CELL(0, sD, saD, sI, saI, sB, sA, ob, oa, od, oad, oi, oai, ot)                                                 \
+      cB[y] = ob; cA[y] = oa; nD[y] = od; naD[y] = oad; nI[y] = oi; naI[y] = oai;                                        \
+      const int k = ob * k256 + (j1 - nlo);                                                                              \
+      lkey = k > lkey ? k : lkey;                                                                                        \
+      B0 = ob; BJ = j1;                                                                                                  \
+      if (TB) tbp[(size_t)d * DP_SLOTS + y] = (unsigned char)ot;                                                         \
+    }                                                                                                                    \
+    wsync();                                                                                                             \
+  }
+
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
 // A(a0 + dirn*(t-1)), likewise B.  forced: the best cell is re-chosen on every diagonal (the DP
 // never gives up); optimal: reaching the far corner only counts if the best score is there.
@@ -239,7 +262,11 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     int lkey = -0x7fffffff;
     const int glo = nlo >> 2, ghi = nhi >> 2;
 #ifdef MFSC_EMU
-    for (int gt = ghi; gt >= glo; gt -= MFSC_LANES) {
+    if (w <= MFSC_LANES) {
+      int e0, ej;
+      DP_PASS1(e0, ej)
+      (void)e0; (void)ej;
+    } else for (int gt = ghi; gt >= glo; gt -= MFSC_LANES) {
       int e0, e1, e2, e3, ej;
       DP_PASS(gt, e0, e1, e2, e3, ej)
       (void)e0; (void)e1; (void)e2; (void)e3; (void)ej;
@@ -248,8 +275,11 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     // a band of at most 248 cells touches at most 63 groups: two passes of 32 lanes, the second one rarely needed.
     // The best-state values of both passes stay in registers for the trim below.
     int t0 = DP_NEG, t1 = DP_NEG, t2 = DP_NEG, t3 = DP_NEG, tj = 0, l0 = DP_NEG, l1 = DP_NEG, l2 = DP_NEG, l3 = DP_NEG, lj = 0;
-    DP_PASS(ghi, t0, t1, t2, t3, tj)
-    if (ghi - glo >= MFSC_LANES) { DP_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+    if (w <= MFSC_LANES) { DP_PASS1(t0, tj) }
+    else {
+      DP_PASS(ghi, t0, t1, t2, t3, tj)
+      if (ghi - glo >= MFSC_LANES) { DP_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+    }
 #endif
     // diagonal maximum, ties to the larger j; its carried word is read back from the best buffer
     const int dkey = wmax_i32(lkey);
@@ -276,7 +306,8 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     for (int g = glo + lane; g <= ghi; g += MFSC_LANES) {
       const int4 v = ld4(cB + ((g * 4) & DP_SMASK));
       const int j0 = g * 4;
-      const unsigned m = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
+      unsigned m = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
+      for (int c = 0; c < 4; c++) if (j0 + c < nlo || j0 + c > nhi) m &= ~(1u << c);   // the narrow pass leaves its neighbours untouched
       if (m) {
         const int a = j0 + dev_ffs32(m) - 1, z = j0 + 31 - dev_clz32(m);
         if (a < lo) lo = a;
