@@ -41,7 +41,10 @@ typedef struct mfsc_params {
   int32_t band_cap;    /* widest DP band kept, <= 248 */
   double diagfactor;   /* -d  0.12 */
   int32_t kmer;        /* index k-mer length, 0 = choose from the reference size */
-  int32_t reserved[3];
+  int32_t engine;      /* stage-4 DP engine: 0 = packed 32-bit states first, reads whose fields do not fit are extended
+                          again by the general engine (same rows either way); 1 = general engine only */
+  int32_t pk_u_span;   /* packed engine: widest spread of the gap-column / mismatch counters over a band that a */
+  int32_t pk_m_span;   /* rebase accepts; 0 = the field capacity.  Smaller values only force more reads to engine 1 */
 } mfsc_params;
 
 typedef struct mfsc_index mfsc_index;     /* contig index resident in HBM */
@@ -113,7 +116,7 @@ int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand,
  * indel (positive: reference base without partner, negative: read base without partner) */
 int mfsc_result_deltas(const mfsc_result* r, int64_t* begin, int64_t* end, int32_t* deltas);
 /* stats[16]: 0 DP cells, 1 DP calls, 2 widest band, 3 probes, 4 matches, 5 kernel launches,
- * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes;
+ * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes, 9 reads handed from the packed to the general DP engine;
  * ms[16]: 0 upload+pack, 1 seeds, 2 sort, 3 cluster, 4 extend, 5 compact+download, 6 total */
 int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]);
 int mfsc_result_free(mfsc_result* r);

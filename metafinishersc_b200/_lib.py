@@ -21,14 +21,15 @@ class Params(ctypes.Structure):
     """mfsc_params; defaults are nucmer's (alignerRobot.py:46-64)."""
     _fields_ = [("minmatch", c_i32), ("mincluster", c_i32), ("maxgap", c_i32), ("breaklen", c_i32), ("diagdiff", c_i32),
                 ("maxmatch", c_i32), ("simplify", c_i32), ("band_cap", c_i32), ("diagfactor", c_dbl), ("kmer", c_i32),
-                ("reserved", c_i32 * 3)]
+                ("engine", c_i32), ("pk_u_span", c_i32), ("pk_m_span", c_i32)]
 
 
 def make_params(minmatch=20, mincluster=65, maxgap=90, breaklen=200, diagdiff=5, diagfactor=0.12, maxmatch=True,
-                simplify=True, band_cap=248, kmer=0):
+                simplify=True, band_cap=248, kmer=0, engine=0, pk_u_span=0, pk_m_span=0):
     p = Params()
     p.minmatch, p.mincluster, p.maxgap, p.breaklen, p.diagdiff = minmatch, mincluster, maxgap, breaklen, diagdiff
     p.maxmatch, p.simplify, p.band_cap, p.diagfactor, p.kmer = int(maxmatch), int(simplify), band_cap, diagfactor, kmer
+    p.engine, p.pk_u_span, p.pk_m_span = engine, pk_u_span, pk_m_span
     return p
 
 

@@ -478,6 +478,8 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
   P.minmatch = p->minmatch; P.mincluster = p->mincluster; P.maxgap = p->maxgap; P.breaklen = p->breaklen; P.diagdiff = p->diagdiff;
   P.maxmatch = p->maxmatch; P.simplify = p->simplify; P.band_cap = p->band_cap; P.diagfactor = p->diagfactor;
   P.k = ix->k; P.stride = p->minmatch - ix->k + 1; P.one = 1;
+  P.pk_u_span = p->pk_u_span > 0 && p->pk_u_span < PK_U_SPAN ? p->pk_u_span : PK_U_SPAN;
+  P.pk_m_span = p->pk_m_span > 0 && p->pk_m_span < PK_M_SPAN ? p->pk_m_span : PK_M_SPAN;
   const SeqStore RS = ix->ref.view(), QS = rd->q.view();
   const int n_reads = rd->n_reads, n_qs = 2 * n_reads;
   Stamp ts[8];
@@ -591,32 +593,47 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       DA(int, r_ref, M); DA(int, r_qry, M); DA(int, r_dir, M); DA(int, r_sA, M); DA(int, r_eA, M); DA(int, r_sB, M); DA(int, r_eB, M);
       DA(int, r_errs, M); DA(int, r_cols, M); DA(int, r_n, n_reads); DA(int, r_off, n_reads + 1);
       DA(int, x_ord, M); DA(int, x_tmp, M); DA(int, x_grp, M); DA(unsigned char, x_fused, M);
-      DA(unsigned long long, d_stats, 4);
-      D.zero(d_stats, sizeof(unsigned long long) * 4);
+      DA(unsigned long long, d_stats, 8);
+      D.zero(d_stats, sizeof(unsigned long long) * 8);
       R0.ref = r_ref; R0.qry = r_qry; R0.dir = r_dir; R0.sA = r_sA; R0.eA = r_eA; R0.sB = r_sB; R0.eB = r_eB; R0.errs = r_errs; R0.cols = r_cols; R0.n_rows = r_n;
+      DA(int, x_retry, n_reads);
       ExtIn I;
       I.seg = seg; I.n_pc = o_npc; I.pc_first = o_pcf; I.pc_n = o_pcn; I.pc_rec = o_pcr; I.cm_s1 = o_s1; I.cm_s2 = o_s2; I.cm_len = o_len;
       I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.grp = x_grp; I.fused = x_fused;
+      I.list = nullptr; I.n_list = nullptr; I.retry = x_retry; I.n_retry = (unsigned*)(d_stats + 4);
       ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2);
       const int ext_block = 128;
       const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
-#ifndef MFSC_EMU
-      cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem);
-#endif
-      // persistent grid: as many blocks as are resident at once, reads handed out by ticket
+      const size_t pk_smem = (size_t)(ext_block / MFSC_LANES) * PK_SMEM_INTS * sizeof(int);
+      // persistent grids: as many blocks as are resident at once, reads handed out by ticket
       unsigned* ext_ticket = (unsigned*)(d_stats + 3);
+      auto resident_grid = [&](const void* fn, size_t smem, int fallback) {
+        unsigned g = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, fallback);
+#ifndef MFSC_EMU
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ext_block, smem) == cudaSuccess && occ > 0)
+          g = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, occ);
+#else
+        (void)fn; (void)smem;
+#endif
+        return g;
+      };
       TbPool pool; pool.tb = nullptr; pool.rev = nullptr; pool.arena = nullptr; pool.arena_ints = 0;
       DeltaOut DO; DO.buf = nullptr; DO.used = nullptr; DO.cap = 0; DO.n_bad = nullptr;
       if (!want_deltas) {
-        unsigned ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, 4);
-#ifndef MFSC_EMU
-        {
-          int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, ext_block, ext_smem) == cudaSuccess && occ > 0)
-            ext_grid = grid_for(D, (long long)n_reads * MFSC_LANES, ext_block, occ);
+        const unsigned ext_grid = resident_grid((const void*)k_extend<false, false>, ext_smem, 4);
+        if (p->engine == 1) {
+          MFSC_LAUNCH((k_extend<false, false>), ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+        } else {
+          // packed engine over every read, then the general engine over the reads it handed back (usually none)
+          const unsigned pk_grid = resident_grid((const void*)k_extend<false, true>, pk_smem, 8);
+          MFSC_LAUNCH((k_extend<false, true>), pk_grid, ext_block, pk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+          D.launches++;
+          ExtIn I2 = I;
+          I2.list = x_retry; I2.n_list = I.n_retry; I2.retry = nullptr; I2.n_retry = nullptr;
+          MFSC_LAUNCH((k_extend<false, false>), ext_grid, ext_block, ext_smem, D.stream, RS, QS, I2, n_reads, P, R0, st, ext_ticket + 1, pool, DO);
         }
-#endif
-        MFSC_LAUNCH(k_extend<false>, ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
       } else {
         // delta mode: the kernel instantiation that records one traceback byte per cell (mfsc_extend.cuh)
 #ifdef MFSC_EMU
@@ -624,11 +641,11 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         const size_t tb_smem = 0;
 #else
         const int tb_block = ext_block; const size_t tb_smem = ext_smem;
-        cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem);
+        cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem);
         unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 4);
         {
           int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true>, tb_block, tb_smem) == cudaSuccess && occ > 0)
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, false>, tb_block, tb_smem) == cudaSuccess && occ > 0)
             tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, occ);
         }
 #endif
@@ -646,7 +663,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         pool.tb = p_tb; pool.rev = p_rev; pool.arena = p_arena;
         DO.buf = d_delta; DO.used = d_used; DO.cap = dcap; DO.n_bad = (unsigned*)(d_used + 1);
         R0.head = x_head; R0.tail = x_tail; R0.dl_begin = x_dlb; R0.dl_end = x_dle;
-        MFSC_LAUNCH(k_extend<true>, tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+        MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
       }
       D.launches++;
       stamp(D, ts[4]);
@@ -680,8 +697,9 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         D.d2h(res->deltas.data(), DO.buf, sizeof(int) * used[0]);
         D.d2h(res->dl_b.data(), c_dlb, sizeof(int) * n_rows); D.d2h(res->dl_e.data(), c_dle, sizeof(int) * n_rows);
       }
-      unsigned long long hst[4];
+      unsigned long long hst[8];
       D.d2h(hst, d_stats, sizeof(hst));
+      res->stats[9] = (int64_t)(hst[4] & 0xffffffffull);
       res->stats[0] = (int64_t)hst[0]; res->stats[1] = (int64_t)hst[1]; res->stats[2] = (int64_t)(int)(hst[2] & 0xffffffffull);
       res->stats[8] = n_rows * 32 + 8;
       stamp(D, ts[5]);

@@ -71,6 +71,7 @@ struct ExtCtx {
   SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
   mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw;   // per-warp statistics, flushed once per kernel
   mutable TbCtx T;
+  mutable int pk_fail;           // packed engine only: a field did not fit, the read goes to the general engine
   SeqView A; SeqView B[2];
   RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
   const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
@@ -199,6 +200,37 @@ MFSC_DEV void st4(int* p, int a, int b, int c, int d) { int4 v; v.x = a; v.y = b
     }                                                                                                                    \
     wsync();                                                                                                             \
   }
+
+// Walk the traceback codes of the current DP back from the finish cell; the columns land in E.T.rev, last column
+// first.  Returns their number (all lanes).
+MFSC_DEV int dp_traceback(const ExtCtx& E, int FinD, int FinJ) {
+  const unsigned char* tbp = E.T.tb;
+  wsync();
+  int n = 0;
+  if (E.lane == 0) {
+    unsigned char* rev = E.T.rev;
+    int dd = FinD, jj = FinJ;
+    int s = dd > 0 ? (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u) : 2;
+    while (dd > 0 && n < TB_DIAGS) {
+      if (s == 2) {
+        rev[n++] = 0; dd -= 2; jj -= 1;
+        if (dd > 0) s = (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u);
+      } else if (s == 0) {
+        rev[n++] = 2; dd -= 1; jj -= 1;
+        const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
+        s = (pc & 4u) ? 0 : (int)(pc & 3u);
+      } else {
+        rev[n++] = 1; dd -= 1;
+        const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
+        s = (pc & 8u) ? 1 : (int)(pc & 3u);
+      }
+    }
+    if (dd != 0) E.T.bad = 1;
+  }
+  n = wbcast_i32(n, 0);
+  wsync();
+  return n;
+}
 
 // Cell (i,j): i bases of A and j bases of B consumed, anti-diagonal d = i + j.  A base t (1..N) is
 // A(a0 + dirn*(t-1)), likewise B.  forced: the best cell is re-chosen on every diagonal (the DP
@@ -351,35 +383,16 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
     E.acc_cells += cells; E.acc_calls += 1ull;
     if (maxw > E.acc_maxw) E.acc_maxw = maxw;
   }
-  o.n_ops = 0;
-  if (TB && want_ops) {
-    // walk back from the finish cell; the columns land in E.T.rev, last column first
-    wsync();
-    int n = 0;
-    if (lane == 0) {
-      unsigned char* rev = E.T.rev;
-      int dd = FinD, jj = FinJ;
-      int s = dd > 0 ? (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u) : 2;
-      while (dd > 0 && n < TB_DIAGS) {
-        if (s == 2) {
-          rev[n++] = 0; dd -= 2; jj -= 1;
-          if (dd > 0) s = (int)(tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)] & 3u);
-        } else if (s == 0) {
-          rev[n++] = 2; dd -= 1; jj -= 1;
-          const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
-          s = (pc & 4u) ? 0 : (int)(pc & 3u);
-        } else {
-          rev[n++] = 1; dd -= 1;
-          const unsigned pc = tbp[(size_t)dd * DP_SLOTS + (jj & DP_SMASK)];
-          s = (pc & 8u) ? 1 : (int)(pc & 3u);
-        }
-      }
-      if (dd != 0) E.T.bad = 1;
-    }
-    o.n_ops = wbcast_i32(n, 0);
-    wsync();
-  }
+  o.n_ops = (TB && want_ops) ? dp_traceback(E, FinD, FinJ) : 0;
   return o;
+}
+
+#include "mfsc_extend_pk.cuh"
+
+template <bool TB, bool PK>
+MFSC_DEV DpOut dp_run(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N, int M, bool forced, bool optimal, bool want_ops) {
+  if (PK) return dp_engine_pk<TB>(E, dir, a0, b0, dirn, N, M, forced, optimal, want_ops);
+  return dp_engine<TB>(E, dir, a0, b0, dirn, N, M, forced, optimal, want_ops);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,13 +470,13 @@ MFSC_DEV int c_s1(const ExtCtx& E, int c, int t) { return (int)(E.cm_s1[E.pc_fir
 MFSC_DEV int c_s2(const ExtCtx& E, int c, int t) { return E.cm_s2[E.pc_first[E.ord[c]] + t] + 1; }
 MFSC_DEV int c_len(const ExtCtx& E, int c, int t) { return E.cm_len[E.pc_first[E.ord[c]] + t]; }
 
-template <bool TB>
+template <bool TB, bool PK>
 MFSC_DEV bool ext_forward(ExtCtx& E, int ci, int tA, int tB, bool forced, bool optimal) {
   const int eA = E.R.eA[ci], eB = E.R.eB[ci], dir = E.R.dir[ci];
   bool overflow = false;
   if (tA - eA + 1 > DP_MAX_ALN) { tA = eA + DP_MAX_ALN - 1; overflow = true; optimal = true; }
   if (tB - eB + 1 > DP_MAX_ALN) { tB = eB + DP_MAX_ALN - 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine<TB>(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal, true);
+  DpOut o = dp_run<TB, PK>(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal, true);
   // the DP re-aligns the alignment's last column
   wsync();
   if (E.lane == 0) {
@@ -475,18 +488,18 @@ MFSC_DEV bool ext_forward(ExtCtx& E, int ci, int tA, int tB, bool forced, bool o
   return o.reached && !overflow;
 }
 
-template <bool TB>
+template <bool TB, bool PK>
 MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
   const int sA = E.R.sA[ci], sB = E.R.sB[ci], dir = E.R.dir[ci];
   int tA, tB; bool optimal = false, overflow = false;
   if (ti >= 0) { tA = E.R.eA[ti]; tB = E.R.eB[ti]; } else { tA = 1; tB = 1; optimal = true; }
   if (sA - tA + 1 > DP_MAX_ALN) { tA = sA - DP_MAX_ALN + 1; overflow = true; optimal = true; }
   if (sB - tB + 1 > DP_MAX_ALN) { tB = sB - DP_MAX_ALN + 1; overflow = true; optimal = true; }
-  DpOut o = dp_engine<TB>(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal, false);
+  DpOut o = dp_run<TB, PK>(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal, false);
   bool reached = o.reached;
   if (overflow || ti < 0) reached = false;
   if (reached) {
-    ext_forward<TB>(E, ti, sA, sB, true, false);
+    ext_forward<TB, PK>(E, ti, sA, sB, true, false);
     // the target now ends on this alignment's first column; append the rest and drop this alignment
     if (E.lane == 0) {
       E.R.cols[ti] += E.R.cols[ci] - 1; E.R.errs[ti] += E.R.errs[ci];
@@ -500,7 +513,7 @@ MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
     E.al1--;
   } else {
     const int nsA = sA - o.fi + 1, nsB = sB - o.fj + 1;
-    DpOut o2 = dp_engine<TB>(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false, true);
+    DpOut o2 = dp_run<TB, PK>(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false, true);
     wsync();
     if (E.lane == 0) {
       E.R.cols[ci] += o2.cols - 1; E.R.errs[ci] += o2.errs;
@@ -562,7 +575,7 @@ MFSC_DEV int ext_reverse_target(const ExtCtx& E, int cur) {
 }
 
 // Walk the clusters of one (record, read) group in order; returns nothing, alignments are rows [al0, al1)
-template <bool TB>
+template <bool TB, bool PK>
 MFSC_DEV void ext_clusters(ExtCtx& E) {
   bool target_reached = false;
   int tA = 0, tB = 0;
@@ -598,15 +611,15 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
         }
         wsync();
         const int ti = ext_reverse_target(E, curA);
-        if (ext_backward<TB>(E, curA, ti)) curA = ti;
+        if (ext_backward<TB, PK>(E, curA, ti)) curA = ti;
       }
       if (mi < nm - 1) {
         tA = c_s1(E, cur, mi + 1); tB = c_s2(E, cur, mi + 1);
-        target_reached = ext_forward<TB>(E, curA, tA, tB, false, false);
+        target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, false);
       } else {
         tA = E.A.n; tB = E.B[0].n;
         targetC = ext_forward_target(E, cur, tA, tB);
-        target_reached = ext_forward<TB>(E, curA, tA, tB, false, targetC < 0);
+        target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, targetC < 0);
       }
     }
     if (targetC < 0) target_reached = false;
@@ -623,6 +636,9 @@ struct ExtIn {
   const unsigned* cm_s1; const int* cm_s2; const int* cm_len;
   const unsigned* r_ostart;             // [n_ref]
   int* ord; int* key_tmp; int* grp; unsigned char* fused;   // scratch (per-match slices)
+  // reads to extend: all of them (list == nullptr) or list[0 .. *n_list).  The packed-engine instantiation appends the
+  // reads it has to hand over to the general engine to retry[0 .. *n_retry).
+  const int* list; const unsigned* n_list; int* retry; unsigned* n_retry;
 };
 
 #ifdef MFSC_EMU
@@ -632,25 +648,30 @@ static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #ifndef MFSC_EXT_MINBLOCKS
 #define MFSC_EXT_MINBLOCKS 6
 #endif
+#ifndef MFSC_EXT_MINBLOCKS_PK
+#define MFSC_EXT_MINBLOCKS_PK 8
+#endif
 struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; int arena_ints; };
 
-template <bool TB>
-MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
+template <bool TB, bool PK>
+MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
                                                    unsigned* ticket, TbPool pool, DeltaOut DO) {
 #ifdef MFSC_EMU
   int* sm = emu_dp_smem;
 #else
   extern __shared__ int4 dp_smem4[];
-  int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * DP_SMEM_INTS;
+  int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * (PK ? PK_SMEM_INTS : DP_SMEM_INTS);
 #endif
   const int lane = lane_id();
   unsigned long long w_cells = 0, w_calls = 0; int w_maxw = 0;
+  const int n_work = I.list ? (int)*I.n_list : n_reads;
   // reads are handed out by a ticket counter: a warp takes the next read when it is done with its own
   for (;;) {
     int q = 0;
     if (lane == 0) q = (int)atomic_add_u32(ticket, 1u);
     q = wbcast_i32(q, 0);
-    if (q >= n_reads) break;
+    if (q >= n_work) break;
+    if (I.list) q = I.list[q];
     const int b0 = I.seg[2 * q], b1 = I.seg[2 * q + 1];
     const int n0 = I.n_pc[2 * q], n1 = I.n_pc[2 * q + 1];
     const int nC = n0 + n1;
@@ -697,6 +718,7 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
     E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0;
     E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.cap = 0; E.T.top = 0; E.T.bad = 0;
+    E.pk_fail = 0;
     if (TB) {
       const long long wg = warp_global();
       E.T.tb = pool.tb + (size_t)wg * TB_DIAGS * DP_SLOTS;
@@ -717,11 +739,16 @@ MFSC_KERNEL_LB(128, MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn
       E.ord = ord + g0; E.nC = g1 - g0;
       E.A.base = RS.start[rec]; E.A.n = RS.len[rec]; E.a_ostart = I.r_ostart[rec]; E.ref_id = rec;
       E.al0 = row0 + rows; E.al1 = E.al0;
-      ext_clusters<TB>(E);
+      ext_clusters<TB, PK>(E);
       rows = E.al1 - row0;
       g0 = g1;
     }
     wsync();
+    if (PK && E.pk_fail) {
+      // a DP of this read did not fit the packed words: nothing of it is kept, the general engine extends it again
+      if (lane == 0) { R.n_rows[q] = 0; I.retry[atomic_add_u32(I.n_retry, 1u)] = q; }
+      continue;
+    }
     // reverse-strand rows are reported on the forward read: position p -> qlen - p + 1
     const int qlen = QS.len[2 * q];
     for (int x = lane; x < rows; x += MFSC_LANES) {

@@ -1,0 +1,307 @@
+// mfsc_extend_pk.cuh -- the packed DP engine of stage 4 (included by mfsc_extend.cuh).
+//
+// Same recurrence, band rule, tie rule and result as dp_engine in mfsc_extend.cuh, with every DP state held in ONE
+// 32-bit word so that a three-way selection is one integer maximum instead of a compare and two selects:
+//
+//     bits 31..19  score (signed, relative: the running best is kept near PK_H0 by periodic rebasing)
+//     bits 18..17  state priority, only meaningful inside a comparison (M 2, I 1, D 0: the tie rule of the
+//                  reference DP -- candidates of one comparison never share (score, priority), so the low bits
+//                  never decide)
+//     bits 16..7   u  = columns of the path that consume B only (relative to the rebasing offset)
+//     bits  6..0   mm = mismatching diagonal columns of the path (relative)
+//
+// At the finish cell (i, j): diagonal columns = j - u, so columns = i + u and errors = mm + i - j + 2u.
+// Every PK_PERIOD anti-diagonals the live words are rebased: the score field by the movement of the running best,
+// u and mm by their minimum over the live band (a path can add at most PK_PERIOD to u and PK_PERIOD/2 to mm in
+// between).  If the spread of u or mm over the band, or the depth of an in-band score below the best, does not
+// fit its field, the engine gives up: the read is then extended again by the general engine (k_extend<TB, false>),
+// so the packing never costs exactness.  Band state: 4 KB + 1 KB of base windows per warp.
+#pragma once
+
+#define PK_SB 19
+#define PK_K (1 << PK_SB)                       // one score unit
+#define PK_P (1 << 17)                          // one priority unit
+#define PK_U1 (1 << 7)                          // one B-only column
+#define PK_CLEAN (~(3 << 17))                   // clears the priority bits
+#define PK_SCORE ((int)0xfff80000)              // the score field
+#define PK_UF(w) (((w) >> 7) & 0x3ff)
+#define PK_MF(w) ((w) & 0x7f)
+#define PK_H0 3000                              // field value the running best is rebased to
+#define PK_SENT (-3500 * PK_K)                  // "unreachable"
+#define PK_FLOOR (-2000)                        // in-band cells must be at least this (field value) at every rebase
+#define PK_PERIOD 64
+#define PK_U_SPAN (1023 - PK_PERIOD - 8)        // widest spread of u / mm over the live band a rebase accepts
+#define PK_M_SPAN (127 - PK_PERIOD / 2 - 4)
+#define PK_MATCH (DP_GOOD * PK_K + 2 * PK_P)
+#define PK_NPAIR (DP_BAD * PK_K + 2 * PK_P)
+#define PK_SMEM_INTS (4 * DP_SLOTS + 2 * DP_WIN / 4)
+
+MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
+
+// one cell: DV = D state handed over by (i, j-1) (priority 0), IV = I state handed over by (i-1, j) (priority 1),
+// RB = best state of (i-1, j-1) (clean).  OB best state (clean), OD / OI what the two gap children receive.
+//   best        : max3(D, I, M)                               M wins ties, then I
+//   towards j+1 : max(D + cont, best + open), one more B-only column;  the open candidate carries priority >= 1
+//   towards i+1 : max(I + cont, best + open);  the open candidate keeps the priority of the best state, so on a
+//                 tie the extension wins exactly when the best state is D
+#define PK_CELL(C, DV, IV, RB, OB, OD, OI, OT)                                                             \
+  {                                                                                                        \
+    const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;               \
+    const int m_ = FADD(RB, nm_ ? PK_NPAIR : PK_MATCH) + (ne_ ? 1 : 0);                                    \
+    const int bu_ = pk_max(pk_max(DV, IV), m_);                                                            \
+    OB = bu_ & PK_CLEAN;                                                                                   \
+    const int c_ = FADD(bu_, DP_GOPEN * PK_K);                                                             \
+    const int cd_ = FADD(c_, PK_U1 + PK_P);                                                                \
+    const int e_ = FADD(DV, DP_GCONT * PK_K + PK_U1);                                                      \
+    const int f_ = FADD(IV, DP_GCONT * PK_K);                                                              \
+    const int du_ = pk_max(e_, cd_), iu_ = pk_max(f_, c_);                                                 \
+    OD = du_ & PK_CLEAN; OI = (iu_ & PK_CLEAN) | PK_P;                                                     \
+    /* traceback code as in DP_CELL: bits 0-1 best state, bit 2 D extended, bit 3 I extended */           \
+    if (TB) OT = (((unsigned)bu_ >> 17) & 3u) | ((((unsigned)du_ >> 17) & 3u) == 0u ? 4u : 0u) | ((((unsigned)iu_ >> 17) & 3u) == 1u ? 8u : 0u); \
+  }
+
+#define PK_PASS(GT, B0, B1, B2, B3, BJ)                                                                                  \
+  {                                                                                                                      \
+    const bool actg = (GT) - lane >= glo;                                                                                \
+    const int g = actg ? (GT) - lane : glo;                                                                              \
+    const int j0 = g * 4;                                                                                                \
+    const int y = j0 & DP_SMASK, y1 = (j0 - 1) & DP_SMASK;                                                               \
+    const int4 vD = ld4(nD + y), vI = ld4(nI + y), vB = ld4(cB + y);                                                     \
+    const int sD = nD[y1], sB = cB[y1];                                                                                  \
+    const int as = d - j0 - 4;                                                                                           \
+    const unsigned w0 = wA32[(as >> 2) & (DP_WIN / 4 - 1)], w1 = wA32[((as >> 2) + 1) & (DP_WIN / 4 - 1)];               \
+    const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);                                                   \
+    const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];                                                              \
+    const unsigned awr = dev_byte_rev(aw);                                                                               \
+    const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);                                                  \
+    wsync();                                                                                                             \
+    if (actg) {                                                                                                          \
+      int o0b, o0d, o0i, o1b, o1d, o1i, o2b, o2d, o2i, o3b, o3d, o3i;                                                    \
+      unsigned o0t = 0, o1t = 0, o2t = 0, o3t = 0;                                                                       \
+      PK_CELL(3, vD.z, vI.w, vB.z, o3b, o3d, o3i, o3t)                                                                   \
+      PK_CELL(2, vD.y, vI.z, vB.y, o2b, o2d, o2i, o2t)                                                                   \
+      PK_CELL(1, vD.x, vI.y, vB.x, o1b, o1d, o1i, o1t)                                                                   \
+      PK_CELL(0, sD, vI.x, sB, o0b, o0d, o0i, o0t)                                                                       \
+      const int r0 = j0 - nlo;                                                                                           \
+      if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = PK_SENT;                                                              \
+      if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = PK_SENT;                                                              \
+      if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = PK_SENT;                                                              \
+      if ((unsigned)r0 >= (unsigned)w) o0b = PK_SENT;                                                                    \
+      st4(cB + y, o0b, o1b, o2b, o3b); st4(nD + y, o0d, o1d, o2d, o3d); st4(nI + y, o0i, o1i, o2i, o3i);                 \
+      lkey = pk_max(lkey, (o3b & PK_SCORE) + (r0 + 3));                                                                  \
+      lkey = pk_max(lkey, (o2b & PK_SCORE) + (r0 + 2));                                                                  \
+      lkey = pk_max(lkey, (o1b & PK_SCORE) + (r0 + 1));                                                                  \
+      lkey = pk_max(lkey, (o0b & PK_SCORE) + r0);                                                                        \
+      B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                   \
+      if (TB) *reinterpret_cast<unsigned*>(tbp + (size_t)d * DP_SLOTS + y) = o0t | (o1t << 8) | (o2t << 16) | (o3t << 24); \
+    }                                                                                                                    \
+    wsync();                                                                                                             \
+  }
+
+#define PK_PASS1(B0, BJ)                                                                                                 \
+  {                                                                                                                      \
+    const bool act1 = lane < w;                                                                                          \
+    const int j1 = act1 ? nhi - lane : nhi;                                                                              \
+    const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;                                                               \
+    const int sD = nD[y1], sI = nI[y], sB = cB[y1];                                                                      \
+    const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
+    const unsigned xm = ca1 ^ cb1, ym = xm | ((ca1 | cb1) & 4u);                                                         \
+    wsync();                                                                                                             \
+    if (act1) {                                                                                                          \
+      int ob, od, oi; unsigned ot = 0;                                                                                   \
+      PK_CELL(0, sD, sI, sB, ob, od, oi, ot)                                                                             \
+      cB[y] = ob; nD[y] = od; nI[y] = oi;                                                                                \
+      lkey = pk_max(lkey, (ob & PK_SCORE) + (j1 - nlo));                                                                 \
+      B0 = ob; BJ = j1;                                                                                                  \
+      if (TB) tbp[(size_t)d * DP_SLOTS + y] = (unsigned char)ot;                                                         \
+    }                                                                                                                    \
+    wsync();                                                                                                             \
+  }
+
+// Returns what dp_engine returns.  When a rebase finds a field out of range E.pk_fail is set and the result is void.
+template <bool TB>
+MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal, bool want_ops) {
+  DpOut o; o.reached = 0; o.fi = 1; o.fj = 1; o.cols = 1; o.errs = 0; o.n_ops = 0;
+  if (E.pk_fail) return o;
+  const int N = wmax_i32(N_), M = wmax_i32(M_);
+  const bool forced = wmax_i32(forced_ ? 1 : 0) != 0;
+  const SeqStore& RS = E.RS; const SeqStore& QS = E.QS; const SeqView Av = E.A; const SeqView Bv = E.B[dir];
+  const DevParams& P = E.P;
+#ifdef MFSC_EMU
+  int* sm = E.sm;
+#else
+  extern __shared__ int4 dp_smem4[];
+  int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * PK_SMEM_INTS;
+#endif
+  const int lane = lane_id();
+  unsigned char* const tbp = TB ? E.T.tb : nullptr;
+  if (TB && lane == 0) tbp[0] = 2;
+  int* nD = sm; int* nI = sm + DP_SLOTS;             // handed to cell (i, j+1) / (i+1, j), stored at j
+  int* bBase = sm + 2 * DP_SLOTS;                    // best state by diagonal parity
+  unsigned char* wA = (unsigned char*)(sm + 4 * DP_SLOTS);
+  unsigned char* wB = wA + DP_WIN;
+  const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
+  const int breaklen = wmax_i32(P.breaklen), band_cap = wmax_i32(P.band_cap), one = P.one;
+  const int u_span = wmax_i32(P.pk_u_span), m_span = wmax_i32(P.pk_m_span);
+  const int max_diff = DP_GOOD * breaklen;
+  wsync();
+  if (lane == 0) {
+    int* b0p = bBase; int* b1p = bBase + DP_SLOTS;
+    nD[0] = (PK_H0 + DP_GOPEN) * PK_K + PK_U1; nI[0] = ((PK_H0 + DP_GOPEN) * PK_K) | PK_P;
+    nD[DP_SMASK] = PK_SENT; nI[1] = PK_SENT;
+    b0p[0] = PK_H0 * PK_K; b0p[DP_SMASK] = PK_SENT; b0p[1] = PK_SENT;
+    b1p[DP_SMASK] = PK_SENT; b1p[0] = PK_SENT; b1p[1] = PK_SENT; b1p[2] = PK_SENT;
+  }
+  int fillA = 0, fillB = 0;
+  dp_fill(RS, Av, a0, dirn, N, 0, 0, wA, lane); fillA = DP_FILL;
+  dp_fill(QS, Bv, b0, dirn, M, 0, 1, wB, lane); fillB = DP_FILL;
+  wsync();
+  int highF = PK_H0, FinD = 0, FinJ = 0, finW = 0, lastW = 0;
+  int accU = 0, accM = 0, dReb = 0, finU = 0, finM = 0, lastU = 0, lastM = 0;   // rebasing offsets and what was recorded before the last rebase
+  int nlo = (1 - N) > 0 ? (1 - N) : 0, nhi = M < 1 ? M : 1;
+  int plo = 0, phi = 0;                                                      // band of the previous diagonal
+  unsigned long long cells = 0;
+  int maxw = 0;
+  int d;
+  for (d = 1; d <= N + M && (d - FinD) <= breaklen && nlo <= nhi; d++) {
+    const int w = nhi - nlo + 1;
+    cells += (unsigned long long)w;
+    if (w > maxw) maxw = w;
+    if (d - nlo > fillA) { dp_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane); fillA += DP_FILL; wsync(); }
+    if (nhi > fillB) { dp_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane); fillB += DP_FILL; wsync(); }
+    int* cB = bBase + (d & 1) * DP_SLOTS;
+    int lkey = -0x7fffffff;
+    const int glo = nlo >> 2, ghi = nhi >> 2;
+#ifdef MFSC_EMU
+    if (w <= MFSC_LANES) {
+      int e0, ej;
+      PK_PASS1(e0, ej)
+      (void)e0; (void)ej;
+    } else for (int gt = ghi; gt >= glo; gt -= MFSC_LANES) {
+      int e0, e1, e2, e3, ej;
+      PK_PASS(gt, e0, e1, e2, e3, ej)
+      (void)e0; (void)e1; (void)e2; (void)e3; (void)ej;
+    }
+#else
+    int t0 = PK_SENT, t1 = PK_SENT, t2 = PK_SENT, t3 = PK_SENT, tj = 0, l0 = PK_SENT, l1 = PK_SENT, l2 = PK_SENT, l3 = PK_SENT, lj = 0;
+    const bool two = ghi - glo >= MFSC_LANES;
+    if (w <= MFSC_LANES) { PK_PASS1(t0, tj) }
+    else {
+      PK_PASS(ghi, t0, t1, t2, t3, tj)
+      if (two) { PK_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+    }
+#endif
+    const int dkey = wmax_i32(lkey);
+    const int dmaxF = dkey >> PK_SB;
+    const int dj = nlo + (dkey & 0xff);
+    const int dW = cB[dj & DP_SMASK];
+    lastW = dW;
+    const bool upd = forced || dmaxF >= highF;
+    highF = upd ? dmaxF : highF; FinD = upd ? d : FinD; FinJ = upd ? dj : FinJ; finW = upd ? dW : finW;
+    {
+      const int hidx = ((lane & 1) ? (nhi + 1) : (nlo - 1)) & DP_SMASK;
+      int* hb = (lane & 2) ? cB : ((lane & 1) ? nI : nD);
+      if (lane < 4 && lane < MFSC_LANES) hb[hidx] = PK_SENT;
+#if MFSC_LANES == 1
+      nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
+#endif
+    }
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    const int thr = (highF - max_diff) * PK_K;      // a clean word is >= thr exactly when its score is
+#ifdef MFSC_EMU
+    wsync();
+    for (int g = glo + lane; g <= ghi; g += MFSC_LANES) {
+      const int4 v = ld4(cB + ((g * 4) & DP_SMASK));
+      const int j0 = g * 4;
+      unsigned m = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
+      for (int c = 0; c < 4; c++) if (j0 + c < nlo || j0 + c > nhi) m &= ~(1u << c);
+      if (m) {
+        const int a = j0 + dev_ffs32(m) - 1, z = j0 + 31 - dev_clz32(m);
+        if (a < lo) lo = a;
+        if (z > hi) hi = z;
+      }
+    }
+#else
+    {
+      const unsigned mt = (t0 >= thr ? 1u : 0u) | (t1 >= thr ? 2u : 0u) | (t2 >= thr ? 4u : 0u) | (t3 >= thr ? 8u : 0u);
+      lo = mt ? tj + dev_ffs32(mt) - 1 : 0x7fffffff;
+      hi = mt ? tj + 31 - dev_clz32(mt) : -0x7fffffff;
+      if (two) {   // the low pass holds smaller j than the top pass
+        const unsigned ml = (l0 >= thr ? 1u : 0u) | (l1 >= thr ? 2u : 0u) | (l2 >= thr ? 4u : 0u) | (l3 >= thr ? 8u : 0u);
+        const int lo_l = ml ? lj + dev_ffs32(ml) - 1 : 0x7fffffff, hi_l = ml ? lj + 31 - dev_clz32(ml) : -0x7fffffff;
+        lo = lo_l < lo ? lo_l : lo;
+        hi = hi > hi_l ? hi : hi_l;
+      }
+    }
+#endif
+    lo = wmin_i32(lo); hi = wmax_i32(hi);
+    wsync();
+    const bool none = lo > hi;
+    if (!none && hi - lo + 2 > band_cap) {
+      int l2 = lo, h2 = hi;
+      while (l2 <= h2 && h2 - l2 + 2 > band_cap) { if ((cB[l2 & DP_SMASK] & PK_SCORE) < (cB[h2 & DP_SMASK] & PK_SCORE)) l2++; else h2--; }
+      lo = wmax_i32(l2); hi = wmax_i32(h2);
+    }
+    if ((d & (PK_PERIOD - 1)) == 0) {
+      // Rebase the live words: what this diagonal wrote (nD, nI, its best buffer over [nlo, nhi]) and the best buffer
+      // of the previous diagonal over its own band.  Everything else in reach of the next diagonals is halo and is
+      // rewritten as a sentinel; slots further out hold leftovers of earlier diagonals (or earlier DPs) that nobody
+      // reads before they are written again.
+      int* cP = bBase + ((d + 1) & 1) * DP_SLOTS;
+      const int rlo = (plo < nlo ? plo : nlo) - 1, rhi = (phi > nhi ? phi : nhi) + 1;
+      int mnU = 0x7fffffff, mxU = 0, mnM = 0x7fffffff, mxM = 0, mnS = 0x7fffffff;
+      for (int j = rlo + lane; j <= rhi; j += MFSC_LANES) {
+        const int y = j & DP_SMASK;
+        const bool inD = j >= nlo && j <= nhi, inP = j >= plo && j <= phi;
+        const int a[4] = {nD[y], nI[y], cB[y], cP[y]};
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (t < 3 ? inD : inP) {
+            const int u_ = PK_UF(a[t]), m_ = PK_MF(a[t]);
+            mnU = u_ < mnU ? u_ : mnU; mxU = u_ > mxU ? u_ : mxU; mnM = m_ < mnM ? m_ : mnM; mxM = m_ > mxM ? m_ : mxM;
+          }
+        // in-band cells are never sentinels; the handed-over gap states and the previous diagonal lie at most a few
+        // gap penalties below the best states checked here
+        if (inD) { const int s = a[2] >> PK_SB; mnS = s < mnS ? s : mnS; }
+        if (inP) { const int s = a[3] >> PK_SB; mnS = s < mnS ? s : mnS; }
+      }
+      mnU = wmin_i32(mnU); mxU = wmax_i32(mxU); mnM = wmin_i32(mnM); mxM = wmax_i32(mxM); mnS = wmin_i32(mnS);
+      if (mxU - mnU > u_span || mxM - mnM > m_span || mnS < PK_FLOOR) { E.pk_fail = 1; return o; }
+      if (FinD > dReb) { finU = PK_UF(finW) + accU; finM = PK_MF(finW) + accM; }
+      lastU = PK_UF(lastW) + accU; lastM = PK_MF(lastW) + accM;
+      const int delta = (highF - PK_H0) * PK_K + mnU * PK_U1 + mnM;
+      accU += mnU; accM += mnM; dReb = d; highF = PK_H0;
+      wsync();
+      for (int j = rlo + lane; j <= rhi; j += MFSC_LANES) {
+        const int y = j & DP_SMASK;
+        const bool inD = j >= nlo && j <= nhi, inP = j >= plo && j <= phi;
+        nD[y] = inD ? nD[y] - delta : PK_SENT;
+        nI[y] = inD ? nI[y] - delta : PK_SENT;
+        cB[y] = inD ? cB[y] - delta : PK_SENT;
+        cP[y] = inP ? cP[y] - delta : PK_SENT;
+      }
+      wsync();
+    }
+    plo = nlo; phi = nhi;
+    {
+      const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;
+      nlo = none ? 1 : (lo > a ? lo : a);
+      nhi = none ? 0 : (hi + 1 < t ? hi + 1 : t);
+    }
+  }
+  const int dlast = d - 1;
+  if (FinD > dReb) { finU = PK_UF(finW) + accU; finM = PK_MF(finW) + accM; }
+  if (dlast > dReb) { lastU = PK_UF(lastW) + accU; lastM = PK_MF(lastW) + accM; }
+  if (dlast == N + M) {
+    if (!optimal) { o.reached = 1; FinD = N + M; FinJ = M; finU = lastU; finM = lastM; }
+    else if (FinD == dlast) o.reached = 1;
+  }
+  o.fi = FinD - FinJ; o.fj = FinJ;
+  o.cols = o.fi + finU; o.errs = finM + o.fi - o.fj + 2 * finU;
+  if (lane == 0) {
+    E.acc_cells += cells; E.acc_calls += 1ull;
+    if (maxw > E.acc_maxw) E.acc_maxw = maxw;
+  }
+  if (TB && want_ops) o.n_ops = dp_traceback(E, FinD, FinJ);
+  return o;
+}

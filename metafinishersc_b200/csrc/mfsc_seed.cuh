@@ -15,6 +15,7 @@ struct DevParams {
   double diagfactor;
   int k, stride;
   int one;   // the integer 1, opaque to the compiler (see FADD in mfsc_extend.cuh)
+  int pk_u_span, pk_m_span;   // packed DP engine: widest field spreads a rebase accepts (mfsc_extend_pk.cuh)
 };
 
 struct ProbeChunk { int qs, pb, pe; };

@@ -66,13 +66,18 @@ def build_cases(scale=1):
     cases.append(("many_identical_records", many, [unit300, rc(unit300), unit300[10:280]] * 14, {}))
     cases.append(("explicit_kmer_8", d["contigs"], mixed[:40], dict(kmer=8)))
     cases.append(("explicit_kmer_14", d["contigs"], mixed[:40], dict(kmer=14)))
+    # DP engines: the general engine alone, and the packed engine with field spans so small that some / all reads are
+    # handed over to the general engine
+    cases.append(("engine_general_only", d2["contigs"], d2["reads"][:10], dict(engine=1)))
+    cases.append(("packed_some_reads_handed_over", d2["contigs"], d2["reads"][:24], dict(pk_m_span=16)))
+    cases.append(("packed_all_reads_handed_over", d2["contigs"], d2["reads"][:8], dict(pk_u_span=100)))
     return cases
 
 
 def run_case(E, O, ref, qry, opts):
     """Run one case through engine E and the oracle O; returns a list of mismatch descriptions."""
     from metafinishersc_b200 import engine
-    okw = {k: v for k, v in opts.items() if k != "kmer"}
+    okw = {k: v for k, v in opts.items() if k not in ("kmer", "engine", "pk_u_span", "pk_m_span")}
     okw.setdefault("band_cap", 248)
     o = O.align(ref, qry, **okw)
     P = engine.make_params(**opts)
