@@ -479,6 +479,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
   P.maxmatch = p->maxmatch; P.simplify = p->simplify; P.band_cap = p->band_cap; P.diagfactor = p->diagfactor;
   P.k = ix->k; P.stride = p->minmatch - ix->k + 1; P.one = 1;
   P.pk_u_span = p->pk_u_span > 0 && p->pk_u_span < PK_U_SPAN ? p->pk_u_span : PK_U_SPAN;
+  P.pk_clean = PK_CLEAN; P.pk_prio = PK_P; P.pk_score = PK_SCORE;
   P.pk_m_span = p->pk_m_span > 0 && p->pk_m_span < PK_M_SPAN ? p->pk_m_span : PK_M_SPAN;
   const SeqStore RS = ix->ref.view(), QS = rd->q.view();
   const int n_reads = rd->n_reads, n_qs = 2 * n_reads;

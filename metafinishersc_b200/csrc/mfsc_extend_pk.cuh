@@ -47,19 +47,23 @@ MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
 #define PK_CELL(C, DV, IV, RB, OB, OD, OI, OT)                                                             \
   {                                                                                                        \
     const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;               \
-    const int m_ = FADD(RB, nm_ ? PK_NPAIR : PK_MATCH) + (ne_ ? 1 : 0);                                    \
+    int m_ = FADD(RB, PK_MATCH);                                                                           \
+    if (nm_) m_ = FADD(m_, PK_NPAIR - PK_MATCH);                                                           \
+    if (ne_) m_ = FADD(m_, 1);                                                                             \
     const int bu_ = pk_max(pk_max(DV, IV), m_);                                                            \
-    OB = bu_ & PK_CLEAN;                                                                                   \
+    OB = bu_ & kclean;                                                                                     \
     const int c_ = FADD(bu_, DP_GOPEN * PK_K);                                                             \
     const int cd_ = FADD(c_, PK_U1 + PK_P);                                                                \
     const int e_ = FADD(DV, DP_GCONT * PK_K + PK_U1);                                                      \
     const int f_ = FADD(IV, DP_GCONT * PK_K);                                                              \
     const int du_ = pk_max(e_, cd_), iu_ = pk_max(f_, c_);                                                 \
-    OD = du_ & PK_CLEAN; OI = (iu_ & PK_CLEAN) | PK_P;                                                     \
+    OD = du_ & kclean; OI = (iu_ & kclean) | kprio;                                                        \
     /* traceback code as in DP_CELL: bits 0-1 best state, bit 2 D extended, bit 3 I extended */           \
     if (TB) OT = (((unsigned)bu_ >> 17) & 3u) | ((((unsigned)du_ >> 17) & 3u) == 0u ? 4u : 0u) | ((((unsigned)iu_ >> 17) & 3u) == 1u ? 8u : 0u); \
   }
 
+// One pass of the lanes over 32 groups of four cells, highest group GT on lane 0.  Lanes below the band shadow the
+// lowest group: they compute what its lane computes and only their stores are suppressed, so the pass is branch-free.
 #define PK_PASS(GT, B0, B1, B2, B3, BJ)                                                                                  \
   {                                                                                                                      \
     const bool actg = (GT) - lane >= glo;                                                                                \
@@ -75,46 +79,45 @@ MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
     const unsigned awr = dev_byte_rev(aw);                                                                               \
     const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);                                                  \
     wsync();                                                                                                             \
+    int o0b, o0d, o0i, o1b, o1d, o1i, o2b, o2d, o2i, o3b, o3d, o3i;                                                      \
+    unsigned o0t = 0, o1t = 0, o2t = 0, o3t = 0;                                                                         \
+    PK_CELL(3, vD.z, vI.w, vB.z, o3b, o3d, o3i, o3t)                                                                     \
+    PK_CELL(2, vD.y, vI.z, vB.y, o2b, o2d, o2i, o2t)                                                                     \
+    PK_CELL(1, vD.x, vI.y, vB.x, o1b, o1d, o1i, o1t)                                                                     \
+    PK_CELL(0, sD, vI.x, sB, o0b, o0d, o0i, o0t)                                                                         \
+    const int r0 = j0 - nlo;                                                                                             \
+    if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = PK_SENT;                                                                \
+    if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = PK_SENT;                                                                \
+    if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = PK_SENT;                                                                \
+    if ((unsigned)r0 >= (unsigned)w) o0b = PK_SENT;                                                                      \
     if (actg) {                                                                                                          \
-      int o0b, o0d, o0i, o1b, o1d, o1i, o2b, o2d, o2i, o3b, o3d, o3i;                                                    \
-      unsigned o0t = 0, o1t = 0, o2t = 0, o3t = 0;                                                                       \
-      PK_CELL(3, vD.z, vI.w, vB.z, o3b, o3d, o3i, o3t)                                                                   \
-      PK_CELL(2, vD.y, vI.z, vB.y, o2b, o2d, o2i, o2t)                                                                   \
-      PK_CELL(1, vD.x, vI.y, vB.x, o1b, o1d, o1i, o1t)                                                                   \
-      PK_CELL(0, sD, vI.x, sB, o0b, o0d, o0i, o0t)                                                                       \
-      const int r0 = j0 - nlo;                                                                                           \
-      if ((unsigned)(r0 + 3) >= (unsigned)w) o3b = PK_SENT;                                                              \
-      if ((unsigned)(r0 + 2) >= (unsigned)w) o2b = PK_SENT;                                                              \
-      if ((unsigned)(r0 + 1) >= (unsigned)w) o1b = PK_SENT;                                                              \
-      if ((unsigned)r0 >= (unsigned)w) o0b = PK_SENT;                                                                    \
       st4(cB + y, o0b, o1b, o2b, o3b); st4(nD + y, o0d, o1d, o2d, o3d); st4(nI + y, o0i, o1i, o2i, o3i);                 \
-      lkey = pk_max(lkey, (o3b & PK_SCORE) + (r0 + 3));                                                                  \
-      lkey = pk_max(lkey, (o2b & PK_SCORE) + (r0 + 2));                                                                  \
-      lkey = pk_max(lkey, (o1b & PK_SCORE) + (r0 + 1));                                                                  \
-      lkey = pk_max(lkey, (o0b & PK_SCORE) + r0);                                                                        \
-      B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                   \
       if (TB) *reinterpret_cast<unsigned*>(tbp + (size_t)d * DP_SLOTS + y) = o0t | (o1t << 8) | (o2t << 16) | (o3t << 24); \
     }                                                                                                                    \
+    /* lane-local best as (score, cell): ties to the larger j */                                                         \
+    const int kl_ = pk_max(pk_max(pk_max((o3b & kscore) | 3, (o2b & kscore) | 2), (o1b & kscore) | 1), o0b & kscore);    \
+    lkey = pk_max(lkey, kl_ + r0);                                                                                       \
+    B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                     \
     wsync();                                                                                                             \
   }
 
 #define PK_PASS1(B0, BJ)                                                                                                 \
   {                                                                                                                      \
     const bool act1 = lane < w;                                                                                          \
-    const int j1 = act1 ? nhi - lane : nhi;                                                                              \
+    const int j1 = act1 ? nhi - lane : nlo;          /* idle lanes shadow the lowest cell */                             \
     const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;                                                               \
     const int sD = nD[y1], sI = nI[y], sB = cB[y1];                                                                      \
     const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
     const unsigned xm = ca1 ^ cb1, ym = xm | ((ca1 | cb1) & 4u);                                                         \
     wsync();                                                                                                             \
+    int ob, od, oi; unsigned ot = 0;                                                                                     \
+    PK_CELL(0, sD, sI, sB, ob, od, oi, ot)                                                                               \
     if (act1) {                                                                                                          \
-      int ob, od, oi; unsigned ot = 0;                                                                                   \
-      PK_CELL(0, sD, sI, sB, ob, od, oi, ot)                                                                             \
       cB[y] = ob; nD[y] = od; nI[y] = oi;                                                                                \
-      lkey = pk_max(lkey, (ob & PK_SCORE) + (j1 - nlo));                                                                 \
-      B0 = ob; BJ = j1;                                                                                                  \
       if (TB) tbp[(size_t)d * DP_SLOTS + y] = (unsigned char)ot;                                                         \
     }                                                                                                                    \
+    lkey = pk_max(lkey, (ob & kscore) + (j1 - nlo));                                                                     \
+    B0 = ob; BJ = j1;                                                                                                    \
     wsync();                                                                                                             \
   }
 
@@ -143,6 +146,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
   const int breaklen = wmax_i32(P.breaklen), band_cap = wmax_i32(P.band_cap), one = P.one;
   const int u_span = wmax_i32(P.pk_u_span), m_span = wmax_i32(P.pk_m_span);
+  const int kclean = P.pk_clean, kprio = P.pk_prio, kscore = P.pk_score;     // PK_CLEAN, PK_P, PK_SCORE as run-time values: one LOP3 for (x & clean) | prio
   const int max_diff = DP_GOOD * breaklen;
   wsync();
   if (lane == 0) {
@@ -160,12 +164,12 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   int accU = 0, accM = 0, dReb = 0, finU = 0, finM = 0, lastU = 0, lastM = 0;   // rebasing offsets and what was recorded before the last rebase
   int nlo = (1 - N) > 0 ? (1 - N) : 0, nhi = M < 1 ? M : 1;
   int plo = 0, phi = 0;                                                      // band of the previous diagonal
-  unsigned long long cells = 0;
+  unsigned cells = 0;                              // at most 2 * DP_MAX_ALN diagonals of < 256 cells
   int maxw = 0;
   int d;
   for (d = 1; d <= N + M && (d - FinD) <= breaklen && nlo <= nhi; d++) {
     const int w = nhi - nlo + 1;
-    cells += (unsigned long long)w;
+    cells += (unsigned)w;
     if (w > maxw) maxw = w;
     if (d - nlo > fillA) { dp_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane); fillA += DP_FILL; wsync(); }
     if (nhi > fillB) { dp_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane); fillB += DP_FILL; wsync(); }
@@ -299,7 +303,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   o.fi = FinD - FinJ; o.fj = FinJ;
   o.cols = o.fi + finU; o.errs = finM + o.fi - o.fj + 2 * finU;
   if (lane == 0) {
-    E.acc_cells += cells; E.acc_calls += 1ull;
+    E.acc_cells += (unsigned long long)cells; E.acc_calls += 1ull;
     if (maxw > E.acc_maxw) E.acc_maxw = maxw;
   }
   if (TB && want_ops) o.n_ops = dp_traceback(E, FinD, FinJ);

@@ -16,6 +16,7 @@ struct DevParams {
   int k, stride;
   int one;   // the integer 1, opaque to the compiler (see FADD in mfsc_extend.cuh)
   int pk_u_span, pk_m_span;   // packed DP engine: widest field spreads a rebase accepts (mfsc_extend_pk.cuh)
+  int pk_clean, pk_prio, pk_score;   // PK_CLEAN, PK_P, PK_SCORE, opaque to the compiler like `one`
 };
 
 struct ProbeChunk { int qs, pb, pe; };
