@@ -15,7 +15,9 @@
 // u and mm by their minimum over the live band (a path can add at most PK_PERIOD to u and PK_PERIOD/2 to mm in
 // between).  If the spread of u or mm over the band, or the depth of an in-band score below the best, does not
 // fit its field, the engine gives up: the read is then extended again by the general engine (k_extend<TB, false>),
-// so the packing never costs exactness.  Band state: 4 KB + 1 KB of base windows per warp.
+// so the packing never costs exactness.  The same happens when a DP meets a base that is not ACGT: two such bases
+// score as a mismatch without counting as an error, which this engine's single per-cell flag does not express.
+// Band state: 4 KB + 1 KB of base windows per warp.
 #pragma once
 
 #define PK_SB 19
@@ -28,15 +30,28 @@
 #define PK_MF(w) ((w) & 0x7f)
 #define PK_H0 3000                              // field value the running best is rebased to
 #define PK_SENT (-3500 * PK_K)                  // "unreachable"
+#define PK_LIVE (-3000 * PK_K)                  // a word of the previous best buffer below this is a halo sentinel
 #define PK_FLOOR (-2000)                        // in-band cells must be at least this (field value) at every rebase
 #define PK_PERIOD 64
 #define PK_U_SPAN (1023 - PK_PERIOD - 8)        // widest spread of u / mm over the live band a rebase accepts
 #define PK_M_SPAN (127 - PK_PERIOD / 2 - 4)
 #define PK_MATCH (DP_GOOD * PK_K + 2 * PK_P)
-#define PK_NPAIR (DP_BAD * PK_K + 2 * PK_P)
-#define PK_SMEM_INTS (4 * DP_SLOTS + 2 * DP_WIN / 4)
+#define PK_MISM (DP_BAD * PK_K + 2 * PK_P + 1)   // a mismatching pair: score, priority of M, one more mismatch
+#define PK_SMEM_INTS (4 * DP_SLOTS + 2 * DP_WIN / 4 + 4)     // state arrays, base windows, finish-cell record
 
 MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
+
+// dp_fill that also reports whether this lane decoded a base of the sequence proper that is not ACGT
+MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_local, int from, int off, unsigned char* win, int lane) {
+  const int to = from + DP_FILL < n_local + 8 ? from + DP_FILL : n_local + 8;
+  bool bad = false;
+  for (int t = from + lane; t < to; t += MFSC_LANES) {
+    int c = 4;
+    if (t < n_local) { c = code_at(S, V.base + (unsigned)(s0 + dirn * t - 1)); bad |= c > 3; }
+    win[(t + off) & DP_WMASK] = (unsigned char)c;
+  }
+  return bad;
+}
 
 // one cell: DV = D state handed over by (i, j-1) (priority 0), IV = I state handed over by (i-1, j) (priority 1),
 // RB = best state of (i-1, j-1) (clean).  OB best state (clean), OD / OI what the two gap children receive.
@@ -46,10 +61,8 @@ MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
 //                 tie the extension wins exactly when the best state is D
 #define PK_CELL(C, DV, IV, RB, OB, OD, OI, OT)                                                             \
   {                                                                                                        \
-    const bool nm_ = (ym & (0xffu << (8 * C))) != 0u, ne_ = (xm & (0xffu << (8 * C))) != 0u;               \
     int m_ = FADD(RB, PK_MATCH);                                                                           \
-    if (nm_) m_ = FADD(m_, PK_NPAIR - PK_MATCH);                                                           \
-    if (ne_) m_ = FADD(m_, 1);                                                                             \
+    if ((xm & (0xffu << (8 * C))) != 0u) m_ = FADD(m_, PK_MISM - PK_MATCH);                                \
     const int bu_ = pk_max(pk_max(DV, IV), m_);                                                            \
     OB = bu_ & kclean;                                                                                     \
     const int c_ = FADD(bu_, DP_GOPEN * PK_K);                                                             \
@@ -77,7 +90,7 @@ MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
     const unsigned aw = dev_funnel_r(w0, w1, (unsigned)(as & 3) * 8u);                                                   \
     const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];                                                              \
     const unsigned awr = dev_byte_rev(aw);                                                                               \
-    const unsigned xm = awr ^ bw, ym = xm | ((awr | bw) & 0x04040404u);                                                  \
+    const unsigned xm = awr ^ bw;               /* per byte (= cell): non-zero where the two bases differ */             \
     wsync();                                                                                                             \
     int o0b, o0d, o0i, o1b, o1d, o1i, o2b, o2d, o2i, o3b, o3d, o3i;                                                      \
     unsigned o0t = 0, o1t = 0, o2t = 0, o3t = 0;                                                                         \
@@ -108,7 +121,7 @@ MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
     const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;                                                               \
     const int sD = nD[y1], sI = nI[y], sB = cB[y1];                                                                      \
     const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
-    const unsigned xm = ca1 ^ cb1, ym = xm | ((ca1 | cb1) & 4u);                                                         \
+    const unsigned xm = ca1 ^ cb1;                                                                                       \
     wsync();                                                                                                             \
     int ob, od, oi; unsigned ot = 0;                                                                                     \
     PK_CELL(0, sD, sI, sB, ob, od, oi, ot)                                                                               \
@@ -157,13 +170,21 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     b1p[DP_SMASK] = PK_SENT; b1p[0] = PK_SENT; b1p[1] = PK_SENT; b1p[2] = PK_SENT;
   }
   int fillA = 0, fillB = 0;
-  dp_fill(RS, Av, a0, dirn, N, 0, 0, wA, lane); fillA = DP_FILL;
-  dp_fill(QS, Bv, b0, dirn, M, 0, 1, wB, lane); fillB = DP_FILL;
+  bool bad = pk_fill(RS, Av, a0, dirn, N, 0, 0, wA, lane); fillA = DP_FILL;
+  bad |= pk_fill(QS, Bv, b0, dirn, M, 0, 1, wB, lane); fillB = DP_FILL;
+  if (wmax_i32(bad ? 1 : 0)) { E.pk_fail = 1; return o; }
   wsync();
-  int highF = PK_H0, FinD = 0, FinJ = 0, finW = 0, lastW = 0;
-  int accU = 0, accM = 0, dReb = 0, finU = 0, finM = 0, lastU = 0, lastM = 0;   // rebasing offsets and what was recorded before the last rebase
+  // The finish cell is recorded in shared memory whenever the best score is matched or beaten: (j, word, rebasing
+  // offsets at that time).  The word of the last diagonal's best cell is read back from the best buffer at the end.
+  int* rec = sm + 4 * DP_SLOTS + 2 * DP_WIN / 4;
+  if (lane == 0) { rec[0] = 0; rec[1] = PK_H0 * PK_K; rec[2] = 0; rec[3] = 0; }
+  // halo writer lanes: lane 0 nD[nlo-1], lane 1 nI[nhi+1], lanes 2 and 3 best[nlo-1] and best[nhi+1]
+  int* const halo_base = lane < 2 ? (lane == 0 ? nD : nI) : bBase;
+  const int halo_par = lane >= 2 ? DP_SLOTS : 0;
+  const bool halo_hi = (lane & 1) != 0, halo_on = lane < 4;
+  int highF = PK_H0, FinD = 0;
+  int accU = 0, accM = 0;                          // what the rebases have subtracted from the u / mm fields so far
   int nlo = (1 - N) > 0 ? (1 - N) : 0, nhi = M < 1 ? M : 1;
-  int plo = 0, phi = 0;                                                      // band of the previous diagonal
   unsigned cells = 0;                              // at most 2 * DP_MAX_ALN diagonals of < 256 cells
   int maxw = 0;
   int d;
@@ -171,8 +192,14 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     const int w = nhi - nlo + 1;
     cells += (unsigned)w;
     if (w > maxw) maxw = w;
-    if (d - nlo > fillA) { dp_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane); fillA += DP_FILL; wsync(); }
-    if (nhi > fillB) { dp_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane); fillB += DP_FILL; wsync(); }
+    if (d - nlo > fillA) {
+      if (wmax_i32(pk_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
+      fillA += DP_FILL; wsync();
+    }
+    if (nhi > fillB) {
+      if (wmax_i32(pk_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
+      fillB += DP_FILL; wsync();
+    }
     int* cB = bBase + (d & 1) * DP_SLOTS;
     int lkey = -0x7fffffff;
     const int glo = nlo >> 2, ghi = nhi >> 2;
@@ -198,18 +225,16 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     const int dkey = wmax_i32(lkey);
     const int dmaxF = dkey >> PK_SB;
     const int dj = nlo + (dkey & 0xff);
-    const int dW = cB[dj & DP_SMASK];
-    lastW = dW;
     const bool upd = forced || dmaxF >= highF;
-    highF = upd ? dmaxF : highF; FinD = upd ? d : FinD; FinJ = upd ? dj : FinJ; finW = upd ? dW : finW;
-    {
-      const int hidx = ((lane & 1) ? (nhi + 1) : (nlo - 1)) & DP_SMASK;
-      int* hb = (lane & 2) ? cB : ((lane & 1) ? nI : nD);
-      if (lane < 4 && lane < MFSC_LANES) hb[hidx] = PK_SENT;
+    highF = upd ? dmaxF : highF; FinD = upd ? d : FinD;
+    if (upd && lane == 0) { const int dW = cB[dj & DP_SMASK]; rec[0] = dj; rec[1] = dW; rec[2] = accU; rec[3] = accM; }
+    // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
 #if MFSC_LANES == 1
-      nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
+    nD[(nlo - 1) & DP_SMASK] = PK_SENT; nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
+#else
+    if (halo_on) halo_base[((d & 1) ? halo_par : 0) + (((halo_hi ? nhi + 1 : nlo - 1)) & DP_SMASK)] = PK_SENT;
 #endif
-    }
+    // trim cells that fell more than max_diff below the best (narrows the next diagonal only)
     int lo = 0x7fffffff, hi = -0x7fffffff;
     const int thr = (highF - max_diff) * PK_K;      // a clean word is >= thr exactly when its score is
 #ifdef MFSC_EMU
@@ -227,12 +252,14 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     }
 #else
     {
-      const unsigned mt = (t0 >= thr ? 1u : 0u) | (t1 >= thr ? 2u : 0u) | (t2 >= thr ? 4u : 0u) | (t3 >= thr ? 8u : 0u);
-      lo = mt ? tj + dev_ffs32(mt) - 1 : 0x7fffffff;
-      hi = mt ? tj + 31 - dev_clz32(mt) : -0x7fffffff;
+      // first and last cell of the lane at or above the threshold, as select chains on the four comparisons
+      const bool p0 = t0 >= thr, p1 = t1 >= thr, p2 = t2 >= thr, p3 = t3 >= thr;
+      lo = tj + (p0 ? 0 : (p1 ? 1 : (p2 ? 2 : (p3 ? 3 : 0x40000000))));
+      hi = tj + (p3 ? 3 : (p2 ? 2 : (p1 ? 1 : (p0 ? 0 : -0x40000000))));
       if (two) {   // the low pass holds smaller j than the top pass
-        const unsigned ml = (l0 >= thr ? 1u : 0u) | (l1 >= thr ? 2u : 0u) | (l2 >= thr ? 4u : 0u) | (l3 >= thr ? 8u : 0u);
-        const int lo_l = ml ? lj + dev_ffs32(ml) - 1 : 0x7fffffff, hi_l = ml ? lj + 31 - dev_clz32(ml) : -0x7fffffff;
+        const bool q0 = l0 >= thr, q1 = l1 >= thr, q2 = l2 >= thr, q3 = l3 >= thr;
+        const int lo_l = lj + (q0 ? 0 : (q1 ? 1 : (q2 ? 2 : (q3 ? 3 : 0x40000000))));
+        const int hi_l = lj + (q3 ? 3 : (q2 ? 2 : (q1 ? 1 : (q0 ? 0 : -0x40000000))));
         lo = lo_l < lo ? lo_l : lo;
         hi = hi > hi_l ? hi : hi_l;
       }
@@ -248,45 +275,41 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     }
     if ((d & (PK_PERIOD - 1)) == 0) {
       // Rebase the live words: what this diagonal wrote (nD, nI, its best buffer over [nlo, nhi]) and the best buffer
-      // of the previous diagonal over its own band.  Everything else in reach of the next diagonals is halo and is
-      // rewritten as a sentinel; slots further out hold leftovers of earlier diagonals (or earlier DPs) that nobody
-      // reads before they are written again.
+      // of the previous diagonal over [nlo-1, nhi], the slots the next diagonal reads: each of those is either a cell
+      // of the previous band or one of its two halo sentinels, told apart by value.  The other slots in reach are
+      // halo and are rewritten as sentinels; slots further out hold leftovers nobody reads before they are written again.
       int* cP = bBase + ((d + 1) & 1) * DP_SLOTS;
-      const int rlo = (plo < nlo ? plo : nlo) - 1, rhi = (phi > nhi ? phi : nhi) + 1;
       int mnU = 0x7fffffff, mxU = 0, mnM = 0x7fffffff, mxM = 0, mnS = 0x7fffffff;
-      for (int j = rlo + lane; j <= rhi; j += MFSC_LANES) {
+      for (int j = nlo - 1 + lane; j <= nhi + 1; j += MFSC_LANES) {
         const int y = j & DP_SMASK;
-        const bool inD = j >= nlo && j <= nhi, inP = j >= plo && j <= phi;
+        const bool inD = j >= nlo && j <= nhi;
         const int a[4] = {nD[y], nI[y], cB[y], cP[y]};
+        const bool inP = j <= nhi && a[3] >= PK_LIVE;
 #pragma unroll
         for (int t = 0; t < 4; t++)
           if (t < 3 ? inD : inP) {
             const int u_ = PK_UF(a[t]), m_ = PK_MF(a[t]);
             mnU = u_ < mnU ? u_ : mnU; mxU = u_ > mxU ? u_ : mxU; mnM = m_ < mnM ? m_ : mnM; mxM = m_ > mxM ? m_ : mxM;
           }
-        // in-band cells are never sentinels; the handed-over gap states and the previous diagonal lie at most a few
-        // gap penalties below the best states checked here
+        // the handed-over gap states lie at most a gap penalty below the best states checked here
         if (inD) { const int s = a[2] >> PK_SB; mnS = s < mnS ? s : mnS; }
-        if (inP) { const int s = a[3] >> PK_SB; mnS = s < mnS ? s : mnS; }
       }
       mnU = wmin_i32(mnU); mxU = wmax_i32(mxU); mnM = wmin_i32(mnM); mxM = wmax_i32(mxM); mnS = wmin_i32(mnS);
       if (mxU - mnU > u_span || mxM - mnM > m_span || mnS < PK_FLOOR) { E.pk_fail = 1; return o; }
-      if (FinD > dReb) { finU = PK_UF(finW) + accU; finM = PK_MF(finW) + accM; }
-      lastU = PK_UF(lastW) + accU; lastM = PK_MF(lastW) + accM;
       const int delta = (highF - PK_H0) * PK_K + mnU * PK_U1 + mnM;
-      accU += mnU; accM += mnM; dReb = d; highF = PK_H0;
+      accU += mnU; accM += mnM; highF = PK_H0;
       wsync();
-      for (int j = rlo + lane; j <= rhi; j += MFSC_LANES) {
+      for (int j = nlo - 1 + lane; j <= nhi + 1; j += MFSC_LANES) {
         const int y = j & DP_SMASK;
-        const bool inD = j >= nlo && j <= nhi, inP = j >= plo && j <= phi;
+        const bool inD = j >= nlo && j <= nhi;
+        const int vP = cP[y];
         nD[y] = inD ? nD[y] - delta : PK_SENT;
         nI[y] = inD ? nI[y] - delta : PK_SENT;
         cB[y] = inD ? cB[y] - delta : PK_SENT;
-        cP[y] = inP ? cP[y] - delta : PK_SENT;
+        cP[y] = (j <= nhi && vP >= PK_LIVE) ? vP - delta : PK_SENT;
       }
       wsync();
     }
-    plo = nlo; phi = nhi;
     {
       const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;
       nlo = none ? 1 : (lo > a ? lo : a);
@@ -294,11 +317,14 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     }
   }
   const int dlast = d - 1;
-  if (FinD > dReb) { finU = PK_UF(finW) + accU; finM = PK_MF(finW) + accM; }
-  if (dlast > dReb) { lastU = PK_UF(lastW) + accU; lastM = PK_MF(lastW) + accM; }
+  wsync();
+  int FinJ = rec[0], finW = rec[1], finU = PK_UF(finW) + rec[2], finM = PK_MF(finW) + rec[3];
   if (dlast == N + M) {
-    if (!optimal) { o.reached = 1; FinD = N + M; FinJ = M; finU = lastU; finM = lastM; }
-    else if (FinD == dlast) o.reached = 1;
+    if (!optimal) {
+      // the far corner counts wherever the best score is: its cell is the only one of the last diagonal
+      const int lastW = (bBase + (dlast & 1) * DP_SLOTS)[M & DP_SMASK];
+      o.reached = 1; FinD = N + M; FinJ = M; finU = PK_UF(lastW) + accU; finM = PK_MF(lastW) + accM;
+    } else if (FinD == dlast) o.reached = 1;
   }
   o.fi = FinD - FinJ; o.fj = FinJ;
   o.cols = o.fi + finU; o.errs = finM + o.fi - o.fj + 2 * finU;
