@@ -636,21 +636,18 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
           MFSC_LAUNCH((k_extend<false, false>), ext_grid, ext_block, ext_smem, D.stream, RS, QS, I2, n_reads, P, R0, st, ext_ticket + 1, pool, DO);
         }
       } else {
-        // delta mode: the kernel instantiation that records one traceback byte per cell (mfsc_extend.cuh)
+        // delta mode: the kernel instantiations that record one traceback byte per cell (mfsc_extend.cuh), packed
+        // engine first and the general one over the reads it hands back, like the rows-only path above
+        const bool tb_packed = p->engine != 1;
 #ifdef MFSC_EMU
-        const int tb_block = 32; unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 1);
-        const size_t tb_smem = 0;
+        const int tb_block = 32; const size_t tb_smem = 0, tbpk_smem = 0;
+        const unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 1), tbpk_grid = tb_grid;
 #else
-        const int tb_block = ext_block; const size_t tb_smem = ext_smem;
-        cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem);
-        unsigned tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, 4);
-        {
-          int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, false>, tb_block, tb_smem) == cudaSuccess && occ > 0)
-            tb_grid = grid_for(D, (long long)n_reads * MFSC_LANES, tb_block, occ);
-        }
+        const int tb_block = ext_block; const size_t tb_smem = ext_smem, tbpk_smem = pk_smem;
+        const unsigned tb_grid = resident_grid((const void*)k_extend<true, false>, tb_smem, 4);
+        const unsigned tbpk_grid = tb_packed ? resident_grid((const void*)k_extend<true, true>, tbpk_smem, 6) : 0;
 #endif
-        const size_t n_warps = (size_t)tb_grid * (tb_block / MFSC_LANES);
+        const size_t n_warps = (size_t)std::max(tb_grid, tbpk_grid) * (tb_block / MFSC_LANES);
         // token arena per warp: a read of L bases has at most ~2L columns per alignment, two tokens per indel
         int max_qlen = 0;
         for (int r = 0; r < n_reads; r++) max_qlen = std::max(max_qlen, rd->q.h_len[2 * r]);
@@ -664,7 +661,15 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         pool.tb = p_tb; pool.rev = p_rev; pool.arena = p_arena;
         DO.buf = d_delta; DO.used = d_used; DO.cap = dcap; DO.n_bad = (unsigned*)(d_used + 1);
         R0.head = x_head; R0.tail = x_tail; R0.dl_begin = x_dlb; R0.dl_end = x_dle;
-        MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+        if (!tb_packed) {
+          MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+        } else {
+          MFSC_LAUNCH((k_extend<true, true>), tbpk_grid, tb_block, tbpk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+          D.launches++;
+          ExtIn I2 = I;
+          I2.list = x_retry; I2.n_list = I.n_retry; I2.retry = nullptr; I2.n_retry = nullptr;
+          MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I2, n_reads, P, R0, st, ext_ticket + 1, pool, DO);
+        }
       }
       D.launches++;
       stamp(D, ts[4]);
