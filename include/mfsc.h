@@ -126,6 +126,20 @@ int mfsc_result_free(mfsc_result* r);
 int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows,
                   const int64_t* contig_off, int32_t n_contig, int32_t* cov_out, double ms[2]);
 
+/* The same profile kept resident in HBM for its consumer, the group C-test of the misassembly fixer
+ * (misassemblyFixerLib/mergerHelper.py:137-163 formatIntervalAndFilter: `np.sum(coverageData[start:end])` per candidate
+ * interval; merger.py:189-190 -> mergerHelper.py:84-85 is the 10^7-integer JSON round trip this avoids).
+ * mfsc_cov_interval_sums: sums[q] = sum(cov[contig[q]][start[q]:end[q]]) with Python slice semantics (negative indices
+ * count from the contig end, out-of-range indices are clamped, an empty slice sums to 0), 64-bit.
+ * mfsc_cov_fetch: the profile of one contig (contig >= 0) or of all contigs concatenated (contig = -1). */
+typedef struct mfsc_cov mfsc_cov;
+int mfsc_cov_build(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows,
+                   const int64_t* contig_off, int32_t n_contig, mfsc_cov** out, double ms[2]);
+int mfsc_cov_fetch(const mfsc_cov* c, int32_t contig, int32_t* cov_out);
+int mfsc_cov_interval_sums(const mfsc_cov* c, const int32_t* contig, const int64_t* start, const int64_t* end, int64_t n,
+                           int64_t* sums);
+int mfsc_cov_free(mfsc_cov* c);
+
 /* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
  * delta file of a row set.  names: NUL-separated, one per record.  The delta carries the alignment
  * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors 0`) followed by the indel offset list when the

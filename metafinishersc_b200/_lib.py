@@ -40,7 +40,7 @@ SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_dev
            "mfsc_host_alloc", "mfsc_host_free", "mfsc_index_build", "mfsc_index_create", "mfsc_index_info",
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_reads_upload", "mfsc_reads_free",
            "mfsc_align_reads", "mfsc_align_batch", "mfsc_result_count", "mfsc_result_rows", "mfsc_result_mems",
-           "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_write_coords",
+           "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_cov_build", "mfsc_cov_fetch", "mfsc_cov_interval_sums", "mfsc_cov_free", "mfsc_write_coords",
            "mfsc_write_delta", "mfsc_fasta_parse", "mfsc_fasta_count", "mfsc_fasta_write"]
 
 
@@ -77,6 +77,10 @@ def bind(path):
     L.mfsc_result_stats.argtypes = [c_vp, c_vp, c_vp]
     L.mfsc_result_free.argtypes = [c_vp]
     L.mfsc_coverage.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]
+    L.mfsc_cov_build.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_vp]
+    L.mfsc_cov_fetch.argtypes = [c_vp, c_i32, c_vp]
+    L.mfsc_cov_interval_sums.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]
+    L.mfsc_cov_free.argtypes = [c_vp]
     L.mfsc_write_coords.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_i32, ctypes.c_char_p, c_i32, c_i32]
     L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \

@@ -47,9 +47,9 @@ def select_rows(dataList, SRLenDic):
     return chosen
 
 
-def coverage_from_rows(chosen, LCLenDic, engine=None):
-    """assignCoverage (merger.py:126-140) over all chosen rows at once, on the GPU.
-    Returns {contigName: int32 array}; contigs keep LCLenDic's order."""
+def coverage_profile_from_rows(chosen, LCLenDic, engine=None):
+    """assignCoverage (merger.py:126-140) over all chosen rows at once, on the GPU, left resident in HBM.
+    Returns (engine.CoverageProfile, contig names in LCLenDic's order)."""
     E = engine or alignerRobot.get_engine()
     names = list(LCLenDic.keys())
     cid = {n: i for i, n in enumerate(names)}
@@ -62,11 +62,18 @@ def coverage_from_rows(chosen, LCLenDic, engine=None):
     ref = np.array([cid[r[-2]] for r in rows], dtype=np.int32)
     s1 = np.array([r[0] for r in rows], dtype=np.int32)
     e1 = np.array([r[1] for r in rows], dtype=np.int32)
-    cov = E.coverage(ref, s1, e1, off)
+    return E.coverage_profile(ref, s1, e1, off), names
+
+
+def coverage_from_rows(chosen, LCLenDic, engine=None):
+    """Same, brought back to the host: {contigName: int32 array}; contigs keep LCLenDic's order."""
+    prof, names = coverage_profile_from_rows(chosen, LCLenDic, engine)
+    cov, off = prof.array(), prof.off
+    prof.free()
     return {n: cov[off[i]:off[i + 1]] for i, n in enumerate(names)}
 
 
-def alignSR2LC(folderName, mummerLink, incontigName):
+def alignSR2LC(folderName, mummerLink, incontigName, keep_profile=False):
     """merger.py:142-190: SR.fasta reads vs <incontigName>.fasta contigs -> coveragePerContigs.json."""
     print("alignSR2LC")
     LCLenDic = IORobot.obtainLength(folderName, incontigName + ".fasta")
@@ -74,9 +81,14 @@ def alignSR2LC(folderName, mummerLink, incontigName):
     dataList = alignerRobot.largeRvsQAlign(folderName, 20, mummerLink, referenceName, queryName, outputName)
     SRLenDic = IORobot.obtainLength(folderName, "SR.fasta")
     chosen = select_rows(dataList, SRLenDic)
-    cov = coverage_from_rows(chosen, LCLenDic)
+    prof, names = coverage_profile_from_rows(chosen, LCLenDic)
+    full, off = prof.array(), prof.off
+    cov = {n: full[off[i]:off[i + 1]] for i, n in enumerate(names)}
     with open(folderName + "coveragePerContigs.json", "w") as outfile:
         json.dump({k: v.tolist() for k, v in cov.items()}, outfile)
+    if keep_profile:     # the group C-test's interval sums then run on the device (mergerHelper.groupCTestData)
+        return cov, prof, names
+    prof.free()
     return cov
 
 

@@ -183,6 +183,23 @@ static bool exclusive_sum_i32(Dev& D, const int* in, int* out, long long n) {
 #endif
 }
 
+static bool exclusive_sum_i64(Dev& D, const long long* in, long long* out, long long n) {
+#ifdef MFSC_EMU
+  long long acc = 0;
+  for (long long i = 0; i < n; i++) { long long v = in[i]; out[i] = acc; acc += v; }
+  return true;
+#else
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, D.stream);
+  void* tmp = D.alloc(tmp_bytes);
+  if (!tmp) return false;
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, D.stream);
+  D.free_(tmp);
+  D.launches += 2;
+  return true;
+#endif
+}
+
 static int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
 
 // word layout of a set of sequences (see mfsc_seq.cuh)
@@ -792,9 +809,18 @@ int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]) {
 
 int mfsc_result_free(mfsc_result* r) { delete r; return MFSC_OK; }
 
-int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows, const int64_t* contig_off, int32_t n_contig,
-                  int32_t* cov_out, double ms[2]) {
-  if (n_rows < 0 || !contig_off || n_contig <= 0 || !cov_out) return fail(MFSC_ERR_ARG, "mfsc_coverage: bad arguments");
+struct mfsc_cov {
+  int* cov = nullptr;              // [total] coverage of the concatenated contigs
+  long long* tile_pref = nullptr;  // [n_tiles + 1] exclusive 64-bit prefix of the tile sums
+  long long* off = nullptr;        // [n_contig + 1] device copy of the contig offsets
+  std::vector<long long> h_off;
+  long long total = 0, n_tiles = 0;
+  int n_contig = 0;
+};
+
+int mfsc_cov_build(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows, const int64_t* contig_off, int32_t n_contig,
+                   mfsc_cov** out, double ms[2]) {
+  if (n_rows < 0 || !contig_off || n_contig <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_cov_build: bad arguments");
   Dev& D = g_dev;
   if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
   const long long total = contig_off[n_contig];
@@ -803,32 +829,93 @@ int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, i
     long long len = contig_off[ref_id[r] + 1] - contig_off[ref_id[r]];
     if (s1[r] < 1 || e1[r] > len || s1[r] > e1[r] + 1) return fail(MFSC_ERR_ARG, "mfsc_coverage: interval outside its contig");
   }
-  Stamp t0, t1, t2, t3;
+  Stamp t0, t1, t2;
   stamp(D, t0);
   const long long n_tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+  mfsc_cov* c = new mfsc_cov();
+  c->total = total; c->n_tiles = n_tiles; c->n_contig = n_contig; c->h_off.assign(contig_off, contig_off + n_contig + 1);
   int* d_ref = dalloc<int>(D, n_rows + 1); int* d_s1 = dalloc<int>(D, n_rows + 1); int* d_e1 = dalloc<int>(D, n_rows + 1);
-  long long* d_off = dalloc<long long>(D, n_contig + 1);
-  int* d_diff = dalloc<int>(D, total + 16); int* d_cov = dalloc<int>(D, total + 16);
+  c->off = dalloc<long long>(D, n_contig + 1);
+  int* d_diff = dalloc<int>(D, total + 16); c->cov = dalloc<int>(D, total + 16);
   unsigned long long* d_state = dalloc<unsigned long long>(D, n_tiles + 1);
+  long long* d_tsum = dalloc<long long>(D, n_tiles + 2); c->tile_pref = dalloc<long long>(D, n_tiles + 2);
   unsigned* d_ticket = dalloc<unsigned>(D, 4);
-  if (!d_ref || !d_s1 || !d_e1 || !d_off || !d_diff || !d_cov || !d_state || !d_ticket) return fail(MFSC_ERR_NOMEM, "out of device memory (coverage)");
+  auto release = [&]() { D.free_(d_ref); D.free_(d_s1); D.free_(d_e1); D.free_(d_diff); D.free_(d_state); D.free_(d_tsum); D.free_(d_ticket); };
+  if (!d_ref || !d_s1 || !d_e1 || !c->off || !d_diff || !c->cov || !d_state || !d_tsum || !c->tile_pref || !d_ticket) {
+    release(); mfsc_cov_free(c); return fail(MFSC_ERR_NOMEM, "out of device memory (coverage)");
+  }
   D.h2d(d_ref, ref_id, sizeof(int) * n_rows); D.h2d(d_s1, s1, sizeof(int) * n_rows); D.h2d(d_e1, e1, sizeof(int) * n_rows);
-  D.h2d(d_off, contig_off, sizeof(long long) * (n_contig + 1));
+  D.h2d(c->off, contig_off, sizeof(long long) * (n_contig + 1));
   stamp(D, t1);
   D.zero(d_diff, sizeof(int) * (total + 16)); D.zero(d_state, sizeof(unsigned long long) * (n_tiles + 1)); D.zero(d_ticket, sizeof(unsigned) * 4);
-  if (n_rows > 0) MFSC_LAUNCH(k_cov_diff, grid_for(D, n_rows, 256, 16), 256, 0, D.stream, d_ref, d_s1, d_e1, (long long)n_rows, d_off, total, d_diff);
-  if (total > 0) MFSC_LAUNCH(k_cov_scan, grid_for(D, n_tiles * MFSC_LANES, 256, 8), 256, 0, D.stream, d_diff, total, d_cov, d_state, d_ticket);
-  D.launches += 2;
+  D.zero(d_tsum, sizeof(long long) * (n_tiles + 2));
+  if (n_rows > 0) MFSC_LAUNCH(k_cov_diff, grid_for(D, n_rows, 256, 16), 256, 0, D.stream, d_ref, d_s1, d_e1, (long long)n_rows, c->off, total, d_diff);
+  if (total > 0) {
+    MFSC_LAUNCH(k_cov_scan, grid_for(D, n_tiles * MFSC_LANES, 256, 8), 256, 0, D.stream, d_diff, total, c->cov, d_state, d_ticket);
+    MFSC_LAUNCH(k_cov_tile_sums, grid_for(D, n_tiles * MFSC_LANES, 256, 8), 256, 0, D.stream, c->cov, total, d_tsum);
+  }
+  D.launches += 3;
+  if (!exclusive_sum_i64(D, d_tsum, c->tile_pref, n_tiles + 1)) { release(); mfsc_cov_free(c); return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
   stamp(D, t2);
-  D.d2h(cov_out, d_cov, sizeof(int) * total);
-  stamp(D, t3);
   D.sync();
-  if (ms) { ms[0] = elapsed_ms(D, t1, t2); ms[1] = elapsed_ms(D, t0, t3); }
-  stamp_free(t0); stamp_free(t1); stamp_free(t2); stamp_free(t3);
-  D.free_(d_ref); D.free_(d_s1); D.free_(d_e1); D.free_(d_off); D.free_(d_diff); D.free_(d_cov); D.free_(d_state); D.free_(d_ticket);
+  if (ms) { ms[0] = elapsed_ms(D, t1, t2); ms[1] = elapsed_ms(D, t0, t2); }
+  stamp_free(t0); stamp_free(t1); stamp_free(t2);
+  release();
   std::string msg;
-  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "coverage: " + msg);
+  if (!dev_check(msg)) { mfsc_cov_free(c); return fail(MFSC_ERR_CUDA, "coverage: " + msg); }
+  *out = c;
   return MFSC_OK;
+}
+
+int mfsc_cov_fetch(const mfsc_cov* c, int32_t contig, int32_t* cov_out) {
+  if (!c || !cov_out || contig < -1 || contig >= c->n_contig) return fail(MFSC_ERR_ARG, "mfsc_cov_fetch: bad arguments");
+  Dev& D = g_dev;
+  const long long b = contig < 0 ? 0 : c->h_off[contig], e = contig < 0 ? c->total : c->h_off[contig + 1];
+  D.d2h(cov_out, c->cov + b, sizeof(int) * (size_t)(e - b));
+  std::string msg;
+  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "coverage fetch: " + msg);
+  return MFSC_OK;
+}
+
+int mfsc_cov_interval_sums(const mfsc_cov* c, const int32_t* contig, const int64_t* start, const int64_t* end, int64_t n, int64_t* sums) {
+  if (!c || n < 0 || (n > 0 && (!contig || !start || !end || !sums))) return fail(MFSC_ERR_ARG, "mfsc_cov_interval_sums: bad arguments");
+  for (int64_t q = 0; q < n; q++)
+    if (contig[q] < 0 || contig[q] >= c->n_contig) return fail(MFSC_ERR_ARG, "mfsc_cov_interval_sums: contig id out of range");
+  if (n == 0) return MFSC_OK;
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  int* d_c = dalloc<int>(D, n); long long* d_a = dalloc<long long>(D, n); long long* d_b = dalloc<long long>(D, n); long long* d_s = dalloc<long long>(D, n);
+  if (!d_c || !d_a || !d_b || !d_s) { D.free_(d_c); D.free_(d_a); D.free_(d_b); D.free_(d_s); return fail(MFSC_ERR_NOMEM, "out of device memory (interval sums)"); }
+  D.h2d(d_c, contig, sizeof(int) * n); D.h2d(d_a, start, sizeof(long long) * n); D.h2d(d_b, end, sizeof(long long) * n);
+  MFSC_LAUNCH(k_cov_interval_sums, grid_for(D, n * MFSC_LANES, 256, 8), 256, 0, D.stream, c->cov, c->tile_pref, c->off, d_c, d_a, d_b, (long long)n, d_s);
+  D.launches++;
+  D.d2h(sums, d_s, sizeof(long long) * n);
+  D.free_(d_c); D.free_(d_a); D.free_(d_b); D.free_(d_s);
+  std::string msg;
+  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "interval sums: " + msg);
+  return MFSC_OK;
+}
+
+int mfsc_cov_free(mfsc_cov* c) {
+  if (!c) return MFSC_OK;
+  Dev& D = g_dev;
+  D.free_(c->cov); D.free_(c->tile_pref); D.free_(c->off);
+  delete c;
+  return MFSC_OK;
+}
+
+int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, int64_t n_rows, const int64_t* contig_off, int32_t n_contig,
+                  int32_t* cov_out, double ms[2]) {
+  if (!cov_out) return fail(MFSC_ERR_ARG, "mfsc_coverage: bad arguments");
+  mfsc_cov* c = nullptr;
+  double bms[2] = {0, 0};
+  int rc = mfsc_cov_build(ref_id, s1, e1, n_rows, contig_off, n_contig, &c, bms);
+  if (rc) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  rc = mfsc_cov_fetch(c, -1, cov_out);
+  if (ms) { ms[0] = bms[0]; ms[1] = bms[1] + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+  mfsc_cov_free(c);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -8,6 +8,12 @@
 // The scan is a single-pass chained scan: a warp takes the next tile from a ticket counter, scans
 // it in registers with shuffles, publishes its aggregate and looks back over the preceding tiles'
 // published (flag,value) words, 32 tiles per step.  Traffic: 4 B read + 4 B written per base.
+//
+// The profile can stay resident (mfsc_cov_build): its consumer, the group C-test of the misassembly fixer
+// (misassemblyFixerLib/mergerHelper.py:137-163 formatIntervalAndFilter, `np.sum(coverageData[start:end])` per
+// candidate interval), only needs sums over intervals.  k_cov_tile_sums reduces every 512-base tile to one 64-bit
+// sum (4 B read per base, 8 B written per tile); after an exclusive scan of those, k_cov_interval_sums answers a
+// query with two prefix look-ups and at most two partial tiles.
 #pragma once
 #include "mfsc_platform.cuh"
 
@@ -99,5 +105,52 @@ MFSC_KERNEL k_cov_scan(const int* diff, long long n, int* out, unsigned long lon
 #pragma unroll
       for (int t = 0; t < SCAN_ITEMS; t++) if (base + t < n) out[base + t] = v[t] + lane_off;
     }
+  }
+}
+
+// 64-bit sum of every scan tile of the coverage profile
+MFSC_KERNEL k_cov_tile_sums(const int* cov, long long n, long long* tile_sum) {
+  const int lane = lane_id();
+  const long long n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  for (long long tile = warp_global(); tile < n_tiles; tile += warps_total()) {
+    const long long base = tile * SCAN_TILE;
+    long long s = 0;
+    if (base + SCAN_TILE <= n) {
+      const int4* p = reinterpret_cast<const int4*>(cov + base);
+#pragma unroll
+      for (int t = 0; t < SCAN_ITEMS / 4; t++) { const int4 x = p[t * MFSC_LANES + lane]; s += (long long)x.x + x.y + x.z + x.w; }
+    } else {
+      for (long long i = base + lane; i < n; i += MFSC_LANES) s += cov[i];
+    }
+    s = wsum_i64(s);
+    if (lane == 0) tile_sum[tile] = s;
+  }
+}
+
+// One warp per query: sum of cov[off[c] + a, off[c] + b) with a, b normalised like a Python slice of the contig's list.
+MFSC_KERNEL k_cov_interval_sums(const int* cov, const long long* tile_pref, const long long* contig_off, const int* contig,
+                                const long long* start, const long long* end, long long n_q, long long* out) {
+  const int lane = lane_id();
+  for (long long q = warp_global(); q < n_q; q += warps_total()) {
+    const long long o = contig_off[contig[q]], len = contig_off[contig[q] + 1] - o;
+    long long a = start[q], b = end[q];
+    if (a < 0) a += len;
+    if (b < 0) b += len;
+    a = a < 0 ? 0 : (a > len ? len : a);
+    b = b < 0 ? 0 : (b > len ? len : b);
+    long long s = 0;
+    if (b > a) {
+      a += o; b += o;
+      const long long ta = (a + SCAN_TILE - 1) / SCAN_TILE, tb = b / SCAN_TILE;   // whole tiles [ta, tb)
+      if (ta <= tb) {
+        for (long long i = a + lane; i < ta * SCAN_TILE; i += MFSC_LANES) s += cov[i];
+        for (long long i = tb * SCAN_TILE + lane; i < b; i += MFSC_LANES) s += cov[i];
+        s = wsum_i64(s) + (tile_pref[tb] - tile_pref[ta]);
+      } else {
+        for (long long i = a + lane; i < b; i += MFSC_LANES) s += cov[i];
+        s = wsum_i64(s);
+      }
+    }
+    if (lane == 0) out[q] = s;
   }
 }

@@ -55,6 +55,7 @@ static inline int wmin_i32(int v) { return v; }
 static inline long long wmax_i64(long long v) { return v; }
 static inline long long wmin_i64(long long v) { return v; }
 static inline int wsum_i32(int v) { return v; }
+static inline long long wsum_i64(long long v) { return v; }
 static inline unsigned wballot(bool p) { return p ? 1u : 0u; }
 static inline int wbcast_i32(int v, int) { return v; }
 static inline long long wbcast_i64(long long v, int) { return v; }
@@ -112,6 +113,11 @@ MFSC_DEV long long wmax_i64(long long v) {
 MFSC_DEV long long wmin_i64(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(MFSC_FULL, v, o); v = t < v ? t : v; }
+  return v;
+}
+MFSC_DEV long long wsum_i64(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MFSC_FULL, v, o);
   return v;
 }
 MFSC_DEV unsigned wballot(bool p) { return __ballot_sync(MFSC_FULL, p); }

@@ -83,6 +83,43 @@ class Reads:
             pass
 
 
+class CoverageProfile:
+    """Per-base coverage of a contig set resident in HBM with 64-bit tile prefix sums (mfsc_cov_*): the consumer of
+    merger.assignCoverage's lists, mergerHelper.formatIntervalAndFilter (mergerHelper.py:137-163), only sums intervals."""
+
+    def __init__(self, L, h, contig_off, ms):
+        self.L, self.h, self.off, self.ms = L, h, contig_off, ms
+
+    def contig_len(self, c):
+        return int(self.off[c + 1] - self.off[c])
+
+    def sums(self, contig, start, end):
+        """sum(cov[contig[q]][start[q]:end[q]]) for every q, Python slice semantics, int64."""
+        contig = np.ascontiguousarray(contig, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int64)
+        end = np.ascontiguousarray(end, dtype=np.int64)
+        out = np.zeros(len(contig), dtype=np.int64)
+        check(self.L, self.L.mfsc_cov_interval_sums(self.h, ptr(contig), ptr(start), ptr(end), len(contig), ptr(out)))
+        return out
+
+    def array(self, contig=-1):
+        n = int(self.off[-1]) if contig < 0 else self.contig_len(contig)
+        out = np.zeros(n, dtype=np.int32)
+        check(self.L, self.L.mfsc_cov_fetch(self.h, contig, ptr(out)))
+        return out
+
+    def free(self):
+        if self.h:
+            self.L.mfsc_cov_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, lib=None):
         self.L = lib if lib is not None else _lib.load()
@@ -182,6 +219,18 @@ class Engine:
         check(self.L, self.L.mfsc_coverage(ptr(ref_id), ptr(s1), ptr(e1), len(s1), ptr(contig_off), len(contig_off) - 1,
                                            ptr(cov), ptr(ms)))
         return (cov, ms) if want_ms else cov
+
+    def coverage_profile(self, ref_id, s1, e1, contig_off):
+        """Stage 5 kept resident in HBM: a CoverageProfile answering interval sums on the device."""
+        ref_id = np.ascontiguousarray(ref_id, dtype=np.int32)
+        s1 = np.ascontiguousarray(s1, dtype=np.int32)
+        e1 = np.ascontiguousarray(e1, dtype=np.int32)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
+        h = ctypes.c_void_p()
+        ms = np.zeros(2, dtype=np.float64)
+        check(self.L, self.L.mfsc_cov_build(ptr(ref_id), ptr(s1), ptr(e1), len(s1), ptr(contig_off), len(contig_off) - 1,
+                                            ctypes.byref(h), ptr(ms)))
+        return CoverageProfile(self.L, h, contig_off, ms)
 
     # -- text outputs ----------------------------------------------------------------------
     def write_coords(self, path, rows, ref_names, qry_names, ref_path, qry_path, sort_by_ref=True):

@@ -28,3 +28,8 @@ def test_emu_coverage(emu_engine, oracle):
     cov = emu_engine.coverage(ref, s1, e1, off)
     assert np.array_equal(cov, oracle.coverage(ref, s1, e1, off))
     assert np.array_equal(emu_engine.coverage(ref[:0], s1[:0], e1[:0], off), np.zeros(off[-1], dtype=np.int32))
+
+
+def test_emu_coverage_profile_interval_sums(emu_engine, oracle):
+    from tests import interval_cases
+    interval_cases.run(emu_engine, oracle)

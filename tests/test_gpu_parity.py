@@ -35,6 +35,11 @@ def test_gpu_coverage(gpu_engine, oracle):
     assert np.array_equal(gpu_engine.coverage(ref[:0], s1[:0], e1[:0], off), np.zeros(off[-1], dtype=np.int32))
 
 
+def test_gpu_coverage_profile_interval_sums(gpu_engine, oracle):
+    from tests import interval_cases
+    interval_cases.run(gpu_engine, oracle)
+
+
 def test_gpu_determinism(gpu_engine):
     from metafinishersc_b200 import engine
     name, ref, qry, opts = CASES[1]
