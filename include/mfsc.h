@@ -140,6 +140,25 @@ int mfsc_cov_interval_sums(const mfsc_cov* c, const int32_t* contig, const int64
                            int64_t* sums);
 int mfsc_cov_free(mfsc_cov* c);
 
+/* Row predicates of the reference's consumers (file:line in csrc/mfsc_rowflags.cuh), evaluated for every row at once:
+ * flags[r] = OR of the MFSC_RF_* bits that hold for row r.  ref_len / qry_len: record lengths; ref_gid / qry_gid: an
+ * id per record such that two records carry the same name exactly when their ids are equal (the reference compares
+ * the name strings of columns -2 and -1). */
+#define MFSC_RF_HEADTAIL 1u
+#define MFSC_RF_IDENTICAL 2u
+#define MFSC_RF_ASSOCIATED 4u
+#define MFSC_RF_EMBEDDED_LR 8u
+#define MFSC_RF_REF_COVERED 16u
+#define MFSC_RF_REF_HEAD 32u
+#define MFSC_RF_SHORT_REF 64u
+#define MFSC_RF_SHORT_QRY 128u
+#define MFSC_RF_DIFF_NAME 256u
+#define MFSC_RF_END_SPAN 512u
+#define MFSC_RF_OVERLAP 1024u
+int mfsc_row_flags(int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
+                   const int32_t* s2, const int32_t* e2, const int32_t* ref_len, int32_t n_ref, const int32_t* qry_len,
+                   int32_t n_qry, const int32_t* ref_gid, const int32_t* qry_gid, uint32_t* flags);
+
 /* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
  * delta file of a row set.  names: NUL-separated, one per record.  The delta carries the alignment
  * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors 0`) followed by the indel offset list when the

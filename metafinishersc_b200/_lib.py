@@ -34,13 +34,16 @@ def make_params(minmatch=20, mincluster=65, maxgap=90, breaklen=200, diagdiff=5,
 
 
 KEEP_MEMS, KEEP_CLUSTERS, STOP_SEEDS, STOP_CLUSTERS, WANT_DELTAS = 1, 2, 4, 8, 16
+# mfsc_row_flags bits (include/mfsc.h)
+(RF_HEADTAIL, RF_IDENTICAL, RF_ASSOCIATED, RF_EMBEDDED_LR, RF_REF_COVERED, RF_REF_HEAD, RF_SHORT_REF, RF_SHORT_QRY, RF_DIFF_NAME,
+ RF_END_SPAN, RF_OVERLAP) = [1 << i for i in range(11)]
 
 # every symbol include/mfsc.h declares (tests check the library exports all of them)
 SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_device", "mfsc_default_params",
            "mfsc_host_alloc", "mfsc_host_free", "mfsc_index_build", "mfsc_index_create", "mfsc_index_info",
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_reads_upload", "mfsc_reads_free",
            "mfsc_align_reads", "mfsc_align_batch", "mfsc_result_count", "mfsc_result_rows", "mfsc_result_mems",
-           "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_cov_build", "mfsc_cov_fetch", "mfsc_cov_interval_sums", "mfsc_cov_free", "mfsc_write_coords",
+           "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_cov_build", "mfsc_cov_fetch", "mfsc_cov_interval_sums", "mfsc_cov_free", "mfsc_row_flags", "mfsc_write_coords",
            "mfsc_write_delta", "mfsc_fasta_parse", "mfsc_fasta_count", "mfsc_fasta_write"]
 
 
@@ -81,6 +84,7 @@ def bind(path):
     L.mfsc_cov_fetch.argtypes = [c_vp, c_i32, c_vp]
     L.mfsc_cov_interval_sums.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]
     L.mfsc_cov_free.argtypes = [c_vp]
+    L.mfsc_row_flags.argtypes = [c_i64] + [c_vp] * 7 + [c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]
     L.mfsc_write_coords.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \
         [ctypes.c_char_p, c_i32, ctypes.c_char_p, c_i32, c_i32]
     L.mfsc_write_delta.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_i64] + [c_vp] * 8 + \

@@ -4,6 +4,7 @@
 #include "../../include/mfsc.h"
 #include "mfsc_extend.cuh"
 #include "mfsc_coverage.cuh"
+#include "mfsc_rowflags.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -916,6 +917,36 @@ int mfsc_coverage(const int32_t* ref_id, const int32_t* s1, const int32_t* e1, i
   if (ms) { ms[0] = bms[0]; ms[1] = bms[1] + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
   mfsc_cov_free(c);
   return rc;
+}
+
+int mfsc_row_flags(int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1, const int32_t* s2,
+                   const int32_t* e2, const int32_t* ref_len, int32_t n_ref, const int32_t* qry_len, int32_t n_qry, const int32_t* ref_gid,
+                   const int32_t* qry_gid, uint32_t* flags) {
+  if (n_rows < 0 || n_ref < 0 || n_qry < 0) return fail(MFSC_ERR_ARG, "mfsc_row_flags: bad arguments");
+  if (n_rows == 0) return MFSC_OK;
+  if (!ref_id || !qry_id || !s1 || !e1 || !s2 || !e2 || !ref_len || !qry_len || !ref_gid || !qry_gid || !flags)
+    return fail(MFSC_ERR_ARG, "mfsc_row_flags: bad arguments");
+  for (int64_t r = 0; r < n_rows; r++)
+    if (ref_id[r] < 0 || ref_id[r] >= n_ref || qry_id[r] < 0 || qry_id[r] >= n_qry) return fail(MFSC_ERR_ARG, "mfsc_row_flags: record id out of range");
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  const size_t n = (size_t)n_rows;
+  int* d_rows = dalloc<int>(D, 6 * n); int* d_rl = dalloc<int>(D, 2 * (size_t)n_ref + 1); int* d_ql = dalloc<int>(D, 2 * (size_t)n_qry + 1);
+  unsigned* d_f = dalloc<unsigned>(D, n);
+  auto release = [&]() { D.free_(d_rows); D.free_(d_rl); D.free_(d_ql); D.free_(d_f); };
+  if (!d_rows || !d_rl || !d_ql || !d_f) { release(); return fail(MFSC_ERR_NOMEM, "out of device memory (row flags)"); }
+  const int32_t* cols[6] = {ref_id, qry_id, s1, e1, s2, e2};
+  for (int c = 0; c < 6; c++) D.h2d(d_rows + c * n, cols[c], sizeof(int) * n);
+  D.h2d(d_rl, ref_len, sizeof(int) * n_ref); D.h2d(d_rl + n_ref, ref_gid, sizeof(int) * n_ref);
+  D.h2d(d_ql, qry_len, sizeof(int) * n_qry); D.h2d(d_ql + n_qry, qry_gid, sizeof(int) * n_qry);
+  MFSC_LAUNCH(k_row_flags, grid_for(D, n_rows, 256, 8), 256, 0, D.stream, (long long)n_rows, d_rows, d_rows + n, d_rows + 2 * n, d_rows + 3 * n,
+              d_rows + 4 * n, d_rows + 5 * n, d_rl, d_ql, d_rl + n_ref, d_ql + n_qry, d_f);
+  D.launches++;
+  D.d2h(flags, d_f, sizeof(unsigned) * n);
+  release();
+  std::string msg;
+  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "row flags: " + msg);
+  return MFSC_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -232,6 +232,15 @@ class Engine:
                                             ctypes.byref(h), ptr(ms)))
         return CoverageProfile(self.L, h, contig_off, ms)
 
+    def row_flags(self, rows, ref_len, qry_len, ref_gid, qry_gid):
+        """MFSC_RF_* predicate bits of every row (mfsc_row_flags)."""
+        rl, ql = np.ascontiguousarray(ref_len, dtype=np.int32), np.ascontiguousarray(qry_len, dtype=np.int32)
+        rg, qg = np.ascontiguousarray(ref_gid, dtype=np.int32), np.ascontiguousarray(qry_gid, dtype=np.int32)
+        out = np.zeros(len(rows), dtype=np.uint32)
+        check(self.L, self.L.mfsc_row_flags(len(rows), ptr(rows.ref_id), ptr(rows.qry_id), ptr(rows.s1), ptr(rows.e1), ptr(rows.s2),
+                                            ptr(rows.e2), ptr(rl), len(rl), ptr(ql), len(ql), ptr(rg), ptr(qg), ptr(out)))
+        return out
+
     # -- text outputs ----------------------------------------------------------------------
     def write_coords(self, path, rows, ref_names, qry_names, ref_path, qry_path, sort_by_ref=True):
         rn = b"\0".join(n.encode() for n in ref_names) + b"\0"

@@ -33,3 +33,8 @@ def test_emu_coverage(emu_engine, oracle):
 def test_emu_coverage_profile_interval_sums(emu_engine, oracle):
     from tests import interval_cases
     interval_cases.run(emu_engine, oracle)
+
+
+def test_emu_row_flags(emu_engine):
+    from tests import rowflag_cases
+    rowflag_cases.run(emu_engine)

@@ -40,6 +40,11 @@ def test_gpu_coverage_profile_interval_sums(gpu_engine, oracle):
     interval_cases.run(gpu_engine, oracle)
 
 
+def test_gpu_row_flags(gpu_engine):
+    from tests import rowflag_cases
+    rowflag_cases.run(gpu_engine)
+
+
 def test_gpu_determinism(gpu_engine):
     from metafinishersc_b200 import engine
     name, ref, qry, opts = CASES[1]
