@@ -180,8 +180,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   if (lane == 0) { rec[0] = 0; rec[1] = PK_H0 * PK_K; rec[2] = 0; rec[3] = 0; }
   // halo writer lanes: lane 0 nD[nlo-1], lane 1 nI[nhi+1], lanes 2 and 3 best[nlo-1] and best[nhi+1]
   int* const halo_base = lane < 2 ? (lane == 0 ? nD : nI) : bBase;
-  const int halo_par = lane >= 2 ? DP_SLOTS : 0;
-  const bool halo_hi = (lane & 1) != 0, halo_on = lane < 4;
+  const int halo_par = lane >= 2 ? DP_SLOTS : 0, halo_hi = lane & 1;
   int highF = PK_H0, FinD = 0;
   int accU = 0, accM = 0;                          // what the rebases have subtracted from the u / mm fields so far
   int nlo = (1 - N) > 0 ? (1 - N) : 0, nhi = M < 1 ? M : 1;
@@ -227,13 +226,19 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     const int dj = nlo + (dkey & 0xff);
     const bool upd = forced || dmaxF >= highF;
     highF = upd ? dmaxF : highF; FinD = upd ? d : FinD;
-    if (upd && lane == 0) { const int dW = cB[dj & DP_SMASK]; rec[0] = dj; rec[1] = dW; rec[2] = accU; rec[3] = accM; }
+    // lanes 0..3 write the halo, lane 4 records the finish cell: one predicated store each, no branch.
     // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
+    {
+      const int dW = cB[dj & DP_SMASK];
 #if MFSC_LANES == 1
-    nD[(nlo - 1) & DP_SMASK] = PK_SENT; nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
+      if (upd) st4(rec, dj, dW, accU, accM);
+      nD[(nlo - 1) & DP_SMASK] = PK_SENT; nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
 #else
-    if (halo_on) halo_base[((d & 1) ? halo_par : 0) + (((halo_hi ? nhi + 1 : nlo - 1)) & DP_SMASK)] = PK_SENT;
+      if (upd && lane == 4) st4(rec, dj, dW, accU, accM);
+      int* hp = halo_base + (d & 1) * halo_par + ((nlo - 1 + halo_hi * (w + 1)) & DP_SMASK);
+      if (lane < 4) *hp = PK_SENT;
 #endif
+    }
     // trim cells that fell more than max_diff below the best (narrows the next diagonal only)
     int lo = 0x7fffffff, hi = -0x7fffffff;
     const int thr = (highF - max_diff) * PK_K;      // a clean word is >= thr exactly when its score is
