@@ -282,7 +282,10 @@ def main():
         seed_ms = stage["seeds"] / K
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        ops_per_cell = 40   # integer instructions per DP cell of k_extend's inner loop, counted from SASS
+        # Algorithmic work of one DP cell: the three-state affine-gap recurrence with the two carried counters,
+        # written out on separate words, is 40 integer operations (the count the first version of the kernel issued).  The
+        # packed engine issues about half of that per cell; the figure is kept so that the fraction is comparable over time.
+        ops_per_cell = 40
         alu_peak = n_sm * 128 * sm_mhz * 1e6 / 1e12   # Tiop/s at the clock observed in this run
         ext_tiops = cells * ops_per_cell / (ext_ms * 1e-3) / 1e12 if ext_ms > 0 else 0.0
         out = {
@@ -293,11 +296,12 @@ def main():
                        WORKLOAD if args.reads == 25000 and args.genome == 5_000_000 else
                        "cfg2 shape scaled: %d bp genome, %d reads/GPU" % (args.genome, args.reads),
                        "reads_per_gpu": args.reads, "query_bases_per_gpu": n_bases, "l2": "flushed (256 MiB write) between steps",
+                       "dp_engine": "packed 32-bit states, general engine for handed-over reads" if args.engine == 0 else "general",
                        "index_k": info["k"], "index_hbm_bytes": info["hbm_bytes"], "parallelism": "reads sharded by batch x%d" % world},
             "wall_ms_per_step": wall_ms_max / K,
             "stage_ms_per_step": {k: v / K for k, v in stage.items()},
             "dp_gcups": cells_all / (ext_ms_max / K * 1e-3) / 1e9 if ext_ms_max > 0 else None,
-            "dp_cells_per_step": cells_all, "rows_per_step_rank0": n_rows,
+            "dp_cells_per_step": cells_all, "rows_per_step_rank0": n_rows, "dp_reads_handed_over_rank0": r.stats.get("dp_retry_reads"),
             "index_build_ms": ix.build_ms() if rank == 0 else None, "index_broadcast_ms": bcast_ms, "index_wall_ms": index_wall_ms,
             "e2e": {"value": bases_all * K / (e2e_ms_max * 1e-3) / 1e6, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / K},
@@ -308,9 +312,10 @@ def main():
                          "traffic": (ext_tr["dram_bytes_read"] + ext_tr["dram_bytes_write"]) if ext_tr else None,
                          "pipe_active_ncu": {"alu": ext_tr.get("alu_pipe_active_pct"), "fma": ext_tr.get("fma_pipe_active_pct"),
                                              "issue": ext_tr.get("issue_active_pct"), "source": ext_tr.get("source")} if ext_tr else None,
-                         "note": "banded DP, no HBM traffic to speak of (traffic = ncu dram bytes per launch): cells x %d int ops / kernel time; "
-                                 "peak = %d SMs x 128 lanes x %.0f MHz observed. The binding unit is the ALU pipe (64 lanes/clk/SM), "
-                                 "82%% active in the ncu capture" % (ops_per_cell, n_sm, sm_mhz)},
+                         "note": "banded DP, no HBM traffic to speak of (traffic = ncu dram bytes per launch): cells x %d algorithmic int ops / "
+                                 "kernel time; peak = %d SMs x 128 lanes x %.0f MHz observed. What binds is instruction issue: the ncu capture "
+                                 "(pipe_active_ncu) shows the issue slots and the ALU pipe (64 lanes/clk/SM) about 80 %% busy"
+                                 % (ops_per_cell, n_sm, sm_mhz)},
             "roofline_seed": {"kernel": "k_seeds", "bound": "hbm", "achieved": seed_bytes / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else None,
                               "peak": hbm_peak, "unit": "GB/s", "frac": seed_bytes / (seed_ms * 1e-3) / 1e9 / hbm_peak if seed_ms > 0 else None,
                               "traffic": None, "peak_source": peak_src,
