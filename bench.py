@@ -140,7 +140,7 @@ def run_reference(args, rank, world):
         total_dt += dt; total_bases += sum(len(x) for x in reads); cells += c
     v = total_bases / total_dt / 1e6
     sample = "%d reads (%.1f Mbp) per step of the 25000-read batch, CPU oracle (restatement, not MUMmer)" % (n_sample, total_bases / args.steps / 1e6)
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps,
+    emit(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": total_dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "sample": sample},
@@ -149,7 +149,20 @@ def run_reference(args, rank, world):
                       "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (NCCL's
+    version banner, library chatter) has been diverted to stderr by main()."""
+    os.write(_STDOUT_FD, (line + "\n").encode())
+
+
+_STDOUT_FD = 1
+
+
 def main():
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -328,7 +341,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": threads, "kind": "port",
                                    "sample": "first %d reads of the batch (%.1f s), CPU oracle restatement (MUMmer not in image)" % (n_s, dt),
                                    "dp_gcups": c / dt / 1e9}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
