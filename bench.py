@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", type=int, default=0, help="stage-4 DP engine: 0 packed (+ general for handed-over reads), 1 general only")
+    ap.add_argument("--kmer", type=int, default=0, help="index k-mer length (0: chosen from the reference size)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1"], help="cfg2 is the headline; cfg1 = README shape (parity/aux case)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +194,7 @@ def main():
     E.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    P = engine.make_params(engine=args.engine)
+    P = engine.make_params(engine=args.engine, kmer=args.kmer)
     contigs, reads = make_workload(rank, args.reads if args.workload == "cfg2" else 10**9, args.genome, args.workload)
     buf, off = engine._as_buf(reads)
     n_bases = int(off[-1])

@@ -258,9 +258,15 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
 #else
     {
       // first and last cell of the lane at or above the threshold, as select chains on the four comparisons
-      const bool p0 = t0 >= thr, p1 = t1 >= thr, p2 = t2 >= thr, p3 = t3 >= thr;
-      lo = tj + (p0 ? 0 : (p1 ? 1 : (p2 ? 2 : (p3 ? 3 : 0x40000000))));
-      hi = tj + (p3 ? 3 : (p2 ? 2 : (p1 ? 1 : (p0 ? 0 : -0x40000000))));
+      const bool p0 = t0 >= thr;
+      if (w <= MFSC_LANES) {          // one cell per lane
+        lo = p0 ? tj : 0x40000000;
+        hi = p0 ? tj : -0x40000000;
+      } else {
+        const bool p1 = t1 >= thr, p2 = t2 >= thr, p3 = t3 >= thr;
+        lo = tj + (p0 ? 0 : (p1 ? 1 : (p2 ? 2 : (p3 ? 3 : 0x40000000))));
+        hi = tj + (p3 ? 3 : (p2 ? 2 : (p1 ? 1 : (p0 ? 0 : -0x40000000))));
+      }
       if (two) {   // the low pass holds smaller j than the top pass
         const bool q0 = l0 >= thr, q1 = l1 >= thr, q2 = l2 >= thr, q3 = l3 >= thr;
         const int lo_l = lj + (q0 ? 0 : (q1 ? 1 : (q2 ? 2 : (q3 ? 3 : 0x40000000))));
