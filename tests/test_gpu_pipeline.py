@@ -76,6 +76,30 @@ def test_full_size_properties(gpu_engine):
     ix.free()
 
 
+def test_engines_agree_on_substitution_errors(gpu_engine):
+    """Both DP engines give the same rows on reads with substitutions + indels (the reference's generator makes indels only),
+    at a size the oracle does not finish in seconds; the packed engine does not hand reads over on such data."""
+    rng = np.random.default_rng(7)
+    d = datagen.sc_lr(G=2_000_000, n_reads=1500, seed=100, read_seed=2100, p_del=0.04, p_ins=0.04)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for r in d["reads"]:
+        a = np.frombuffer(r, dtype=np.uint8).copy()
+        m = rng.random(len(a)) < 0.06
+        a[m] = acgt[rng.integers(0, 4, size=int(m.sum()))]
+        reads.append(a.tobytes())
+    out = []
+    for eng in (0, 1):
+        P = engine.make_params(engine=eng)
+        ix = gpu_engine.index(d["contigs"], P)
+        out.append(gpu_engine.align(ix, reads, P))
+        ix.free()
+    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+        assert np.array_equal(getattr(out[0], f), getattr(out[1], f)), f
+    assert out[0].stats["cells"] == out[1].stats["cells"]
+    assert out[0].stats["dp_retry_reads"] == 0 and len(out[0]) >= 1400
+
+
 def test_cfg5_scale_index(gpu_engine):
     """BASELINE cfg 5 shape on the reference side: 100 contigs x 5 Mbp (500 Mbp index, k = 14), one read batch
     drawn from known places.  Property: every read's longest row lands on its source contig and offset."""
