@@ -134,6 +134,84 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     wsync();                                                                                                             \
   }
 
+// ------------------------------------------------------------------------------------------
+// small rectangles
+// ------------------------------------------------------------------------------------------
+// A DP over N x M bases with N + M <= pk_tiny_limit(...) can neither trim its band (no cell can fall 3 * breaklen below
+// the best: the best is at most 3 * floor(d/2) on anti-diagonal d and every cell is at least -6 - 4d, two gaps), nor stop
+// early (fewer anti-diagonals than breaklen), nor meet the band cap: the band is the full rectangle, [max(0, d - N),
+// min(d, M)] on anti-diagonal d.  When the caller takes the far corner wherever the best score is (every DP that is not
+// `optimal`, and every `forced` one), nothing has to be tracked per anti-diagonal at all: the engine below fills the
+// rectangle, one cell per lane and pass, on arrays pre-filled with sentinels (so the borders need no halo), and reads
+// the corner word.  Cells and widest band follow in closed form.  This is the DP between consecutive matches of a
+// cluster on accurate reads (a few bases each), where the per-diagonal bookkeeping of the banded engine is most of the work.
+MFSC_DEV int pk_tiny_limit(int breaklen, int band_cap) {
+  int t = ((DP_GOOD * breaklen - 6) * 2) / 11;
+  if (t > breaklen) t = breaklen;
+  if (t > band_cap - 3) t = band_cap - 3;
+  if (t > DP_FILL - 8) t = DP_FILL - 8;          // one window fill per sequence, and fewer slots than the arrays hold
+  return t;
+}
+
+template <bool TB>
+MFSC_DEV DpOut dp_engine_tiny(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N, int M, bool want_ops, int* sm) {
+  DpOut o; o.reached = 1; o.fi = N; o.fj = M; o.cols = 0; o.errs = 0; o.n_ops = 0;
+  const int lane = lane_id();
+  const DevParams& P = E.P;
+  unsigned char* const tbp = TB ? E.T.tb : nullptr;
+  if (TB && lane == 0) tbp[0] = 2;
+  int* nD = sm; int* nI = sm + DP_SLOTS; int* bBase = sm + 2 * DP_SLOTS;
+  unsigned char* wA = (unsigned char*)(sm + 4 * DP_SLOTS);
+  unsigned char* wB = wA + DP_WIN;
+  const int one = P.one, kclean = P.pk_clean, kprio = P.pk_prio;
+  wsync();
+  // every slot a border cell may read: j in [-1, M + 1] of all four arrays
+  for (int j = -1 + lane; j <= M + 1; j += MFSC_LANES) {
+    const int y = j & DP_SMASK;
+    nD[y] = PK_SENT; nI[y] = PK_SENT; bBase[y] = PK_SENT; bBase[DP_SLOTS + y] = PK_SENT;
+  }
+  bool bad = pk_fill(E.RS, E.A, a0, dirn, N, 0, 0, wA, lane);
+  bad |= pk_fill(E.QS, E.B[dir], b0, dirn, M, 0, 1, wB, lane);
+  if (wmax_i32(bad ? 1 : 0)) { E.pk_fail = 1; o.reached = 0; o.fi = 1; o.fj = 1; o.cols = 1; return o; }
+  wsync();
+  if (lane == 0) {
+    nD[0] = (PK_H0 + DP_GOPEN) * PK_K + PK_U1; nI[0] = ((PK_H0 + DP_GOPEN) * PK_K) | PK_P;
+    bBase[0] = PK_H0 * PK_K;
+  }
+  wsync();
+  for (int d = 1; d <= N + M; d++) {
+    const int nlo = d - N > 0 ? d - N : 0, nhi = d < M ? d : M;
+    int* cB = bBase + (d & 1) * DP_SLOTS;
+    for (int top = nhi; top >= nlo; top -= MFSC_LANES) {
+      const int j1r = top - lane;
+      const bool act1 = j1r >= nlo;
+      const int j1 = act1 ? j1r : nlo;                 // idle lanes shadow the lowest cell
+      const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;
+      const int sD = nD[y1], sI = nI[y], sB = cB[y1];
+      const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];
+      const unsigned xm = ca1 ^ cb1;
+      wsync();
+      int ob, od, oi; unsigned ot = 0;
+      PK_CELL(0, sD, sI, sB, ob, od, oi, ot)
+      if (act1) {
+        cB[y] = ob; nD[y] = od; nI[y] = oi;
+        if (TB) tbp[(size_t)d * DP_SLOTS + y] = (unsigned char)ot;
+      }
+      wsync();
+    }
+  }
+  const int cw = (bBase + ((N + M) & 1) * DP_SLOTS)[M & DP_SMASK];
+  const int u = PK_UF(cw), mm = PK_MF(cw);
+  o.cols = N + u; o.errs = mm + N - M + 2 * u;
+  if (lane == 0) {
+    E.acc_cells += (unsigned long long)(N + 1) * (unsigned long long)(M + 1) - 1ull; E.acc_calls += 1ull;
+    const int mw = (N < M ? N : M) + 1;
+    if (mw > E.acc_maxw) E.acc_maxw = mw;
+  }
+  if (TB && want_ops) o.n_ops = dp_traceback(E, N + M, M);
+  return o;
+}
+
 // Returns what dp_engine returns.  When a rebase finds a field out of range E.pk_fail is set and the result is void.
 template <bool TB>
 MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal, bool want_ops) {
@@ -158,6 +236,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   unsigned char* wB = wA + DP_WIN;
   const unsigned* wA32 = (const unsigned*)wA; const unsigned* wB32 = (const unsigned*)wB;
   const int breaklen = wmax_i32(P.breaklen), band_cap = wmax_i32(P.band_cap), one = P.one;
+  if (N + M <= pk_tiny_limit(breaklen, band_cap) && (forced || !optimal)) return dp_engine_tiny<TB>(E, dir, a0, b0, dirn, N, M, want_ops, sm);
   const int u_span = wmax_i32(P.pk_u_span), m_span = wmax_i32(P.pk_m_span);
   const int kclean = P.pk_clean, kprio = P.pk_prio, kscore = P.pk_score;     // PK_CLEAN, PK_P, PK_SCORE as run-time values: one LOP3 for (x & clean) | prio
   const int max_diff = DP_GOOD * breaklen;
