@@ -142,7 +142,7 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
           const int a = mem[i];
           const long long a_s1 = s1[a], a_s2 = s2[a];
           const int a_len = len[a];
-          long long bestv = (long long)a_len;   // candidates must beat the match alone
+          int bestv = a_len;                    // candidates must beat the match alone
           int bestj = 0x7fffffff, bestadj = 0;
           for (int j = lane; j < i; j += MFSC_LANES) {
             const int c = mem[j];
@@ -152,18 +152,18 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
             if (olap2 > olap) olap = olap2;
             long long pen = olap + ll_abs((a_s2 - a_s1) - ((long long)s2[c] - (long long)s1[c]));
             long long cand = (long long)score[c] + a_len - pen;
-            if (cand > bestv) { bestv = cand; bestj = j; bestadj = (int)olap; }   // first best within the lane
+            // a candidate only matters when it beats a_len > 0, so clamping it from below keeps the comparison exact
+            const int cand32 = cand < -0x40000000ll ? -0x40000000 : (int)cand;
+            if (cand32 > bestv) { bestv = cand32; bestj = j; bestadj = (int)olap; }   // first best within the lane
           }
-          // first best across lanes: max value, then smallest j
-          long long mv = wmax_i64(bestv);
-          int mj = wmin_i32(bestv == mv ? bestj : 0x7fffffff);
+          // first best across lanes: max value, then smallest j; the lane that holds it writes the result
+          const int mv = wmax_i32(bestv);
+          const int mj = wmin_i32(bestv == mv ? bestj : 0x7fffffff);
           if (mj != 0x7fffffff) {
-            int madj = wmax_i32((bestv == mv && bestj == mj) ? bestadj : -0x7fffffff);
-            if (lane == 0) { score[a] = (int)mv; from[a] = mj; adj[a] = madj; }
+            if (bestv == mv && bestj == mj) { score[a] = mv; from[a] = mj; adj[a] = bestadj; flag[a] = 0; }
           } else {
-            if (lane == 0) { score[a] = a_len; from[a] = -1; adj[a] = 0; }
+            if (lane == 0) { score[a] = a_len; from[a] = -1; adj[a] = 0; flag[a] = 0; }
           }
-          if (lane == 0) flag[a] = 0;
           wsync();
         }
         // best chain end: first maximum
