@@ -114,10 +114,11 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     wsync();                                                                                                             \
   }
 
-#define PK_PASS1(B0, BJ)                                                                                                 \
+// One pass of one cell per lane over the CNT cells below and including TOP (CNT <= 32, the lowest one is nlo).
+#define PK_PASS1(TOP, CNT, B0, BJ)                                                                                       \
   {                                                                                                                      \
-    const bool act1 = lane < w;                                                                                          \
-    const int j1 = act1 ? nhi - lane : nlo;          /* idle lanes shadow the lowest cell */                             \
+    const bool act1 = lane < (CNT);                                                                                      \
+    const int j1 = act1 ? (TOP) - lane : nlo;        /* idle lanes shadow the lowest cell */                             \
     const int y = j1 & DP_SMASK, y1 = (j1 - 1) & DP_SMASK;                                                               \
     const int sD = nD[y1], sI = nI[y], sB = cB[y1];                                                                      \
     const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
@@ -284,7 +285,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
 #ifdef MFSC_EMU
     if (w <= MFSC_LANES) {
       int e0, ej;
-      PK_PASS1(e0, ej)
+      PK_PASS1(nhi, w, e0, ej)
       (void)e0; (void)ej;
     } else for (int gt = ghi; gt >= glo; gt -= MFSC_LANES) {
       int e0, e1, e2, e3, ej;
@@ -293,11 +294,18 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     }
 #else
     int t0 = PK_SENT, t1 = PK_SENT, t2 = PK_SENT, t3 = PK_SENT, tj = 0, l0 = PK_SENT, l1 = PK_SENT, l2 = PK_SENT, l3 = PK_SENT, lj = 0;
+    // a band of at most 248 cells touches at most 63 groups: one pass of 32 lanes x 4 cells, and for what is left below
+    // it a pass of one cell per lane when that is at most 32 cells (bands up to ~160 cells), else a second four-cell pass
     const bool two = ghi - glo >= MFSC_LANES;
-    if (w <= MFSC_LANES) { PK_PASS1(t0, tj) }
+    const int low_top = 4 * (ghi - MFSC_LANES + 1) - 1, low_cnt = low_top - nlo + 1;
+    const bool low1 = low_cnt <= MFSC_LANES;
+    if (w <= MFSC_LANES) { PK_PASS1(nhi, w, t0, tj) }
     else {
       PK_PASS(ghi, t0, t1, t2, t3, tj)
-      if (two) { PK_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+      if (two) {
+        if (low1) { PK_PASS1(low_top, low_cnt, l0, lj) }
+        else { PK_PASS(ghi - MFSC_LANES, l0, l1, l2, l3, lj) }
+      }
     }
 #endif
     const int dkey = wmax_i32(lkey);
@@ -347,9 +355,15 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
         hi = tj + (p3 ? 3 : (p2 ? 2 : (p1 ? 1 : (p0 ? 0 : -0x40000000))));
       }
       if (two) {   // the low pass holds smaller j than the top pass
-        const bool q0 = l0 >= thr, q1 = l1 >= thr, q2 = l2 >= thr, q3 = l3 >= thr;
-        const int lo_l = lj + (q0 ? 0 : (q1 ? 1 : (q2 ? 2 : (q3 ? 3 : 0x40000000))));
-        const int hi_l = lj + (q3 ? 3 : (q2 ? 2 : (q1 ? 1 : (q0 ? 0 : -0x40000000))));
+        const bool q0 = l0 >= thr;
+        int lo_l, hi_l;
+        if (low1) {
+          lo_l = q0 ? lj : 0x40000000; hi_l = q0 ? lj : -0x40000000;
+        } else {
+          const bool q1 = l1 >= thr, q2 = l2 >= thr, q3 = l3 >= thr;
+          lo_l = lj + (q0 ? 0 : (q1 ? 1 : (q2 ? 2 : (q3 ? 3 : 0x40000000))));
+          hi_l = lj + (q3 ? 3 : (q2 ? 2 : (q1 ? 1 : (q0 ? 0 : -0x40000000))));
+        }
         lo = lo_l < lo ? lo_l : lo;
         hi = hi > hi_l ? hi : hi_l;
       }
