@@ -4,8 +4,8 @@
 //
 // One warp owns the sorted match list of one (read, strand).  Steps, all in the list's own slice
 // of a few scratch arrays in HBM (a strand's list is short and stays in L1/L2):
-//   1. overlap filter on identical diagonals / identical starts      (sequential, lane 0)
-//   2. union-find over pairs closer than maxgap on near diagonals     (sequential, lane 0)
+//   1. overlap filter on identical diagonals / identical starts      (window scan over the lanes, hits in list order)
+//   2. union-find over pairs closer than maxgap on near diagonals     (window scan over the lanes, unions by lane 0)
 //   3. components ordered by their smallest member                    (counting sort, lane 0)
 //   4. per component, repeatedly: chain DP whose inner "best predecessor" scan is spread over
 //      the lanes and reduced with shuffles, trace back, emit the chain if it covers at least
@@ -51,54 +51,118 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
     int* score = W.score + b; int* adj = W.adj + b; int* from = W.from + b; int* uf = W.uf + b;
     int* ord = W.ord + b; int* tmp = W.tmp + b;
     unsigned char* flag = W.flag + b;
-    int N = 0;
-    if (lane == 0) {
-      // ---- 1. filter ----
-      for (int i = 0; i < n; i++) { s1[i] = m_s1[b + i]; s2[i] = m_s2[b + i]; len[i] = m_len[b + i]; rec[i] = m_rec[b + i]; flag[i] = 1; }
-      for (int i = 0; i < n - 1; i++) {
-        if (!(flag[i] & 1)) continue;
-        long long i_diag = (long long)s2[i] - (long long)s1[i];
-        long long i_end = (long long)s2[i] + len[i];
-        for (int j = i + 1; j < n && s2[j] <= i_end; j++) {
-          if (!(flag[j] & 1)) continue;
-          long long j_diag = (long long)s2[j] - (long long)s1[j];
-          if (i_diag == j_diag) {
-            long long j_extent = (long long)len[j] + s2[j] - s2[i];
-            if (j_extent > len[i]) { len[i] = (int)j_extent; i_end = (long long)s2[i] + j_extent; }
-            flag[j] &= (unsigned char)~1;
-          } else if (s1[i] == s1[j] || s2[i] == s2[j]) {
-            long long olap = (s1[i] == s1[j]) ? ((long long)s2[i] + len[i] - s2[j]) : ((long long)s1[i] + len[i] - (long long)s1[j]);
-            if (len[i] < len[j]) {
-              if (olap >= len[i] / 2) { flag[i] &= (unsigned char)~1; break; }
-            } else if (len[j] < len[i]) {
-              if (olap >= len[j] / 2) flag[j] &= (unsigned char)~1;
-            } else {
-              if (olap >= len[i] / 2) {
-                flag[j] |= 2;
-                if (flag[i] & 2) { flag[i] &= (unsigned char)~1; break; }
-              }
+    // The window scans of steps 1 and 2 (every match against the matches that start inside it / within maxgap
+    // after it: hundreds of candidates per match when many reference records overlap the read, as in all-vs-all read
+    // alignment) are spread over the lanes; the rare candidates that satisfy a condition are then handled one at a time
+    // in list order with the sequential rule, so the result is that of the sequential algorithm.
+    const unsigned all_lanes = MFSC_LANES == 32 ? 0xffffffffu : ((1u << (MFSC_LANES & 31)) - 1u);
+    for (int i = lane; i < n; i += MFSC_LANES) { s1[i] = m_s1[b + i]; s2[i] = m_s2[b + i]; len[i] = m_len[b + i]; rec[i] = m_rec[b + i]; flag[i] = 1; }
+    wsync();
+    // ---- 1. filter ----
+    for (int i = 0; i < n - 1; i++) {
+      unsigned fi = flag[i];
+      if (!(fi & 1)) continue;
+      const long long i_s1 = s1[i], i_s2 = s2[i];
+      const long long i_diag = i_s2 - i_s1;
+      int li = len[i];
+      long long i_end = i_s2 + li;
+      bool changed = false;
+      int j0 = i + 1;
+      while (j0 < n) {
+        const int jj = j0 + lane;
+        const bool in = jj < n && (long long)s2[jj] <= i_end;
+        bool cand = false;
+        if (in && (flag[jj] & 1)) {
+          const long long j_s1 = s1[jj], j_s2 = s2[jj];
+          cand = (j_s2 - j_s1 == i_diag) || j_s1 == i_s1 || j_s2 == i_s2;
+        }
+        const unsigned m = wballot(cand);
+        if (m == 0u) {
+          if (wballot(in) != all_lanes) break;       // the window ends inside this chunk
+          j0 += MFSC_LANES;
+          continue;
+        }
+        const int j = j0 + dev_ffs32(m) - 1;          // first candidate; everything before it is settled
+        const long long j_s1 = s1[j], j_s2 = s2[j];
+        const int lj = len[j];
+        unsigned fj = flag[j];
+        bool stop = false;
+        if (j_s2 - j_s1 == i_diag) {
+          const long long j_extent = (long long)lj + j_s2 - i_s2;
+          if (j_extent > li) { li = (int)j_extent; i_end = i_s2 + j_extent; changed = true; }
+          fj &= ~1u;
+        } else {
+          const long long olap = (i_s1 == j_s1) ? (i_s2 + li - j_s2) : (i_s1 + li - j_s1);
+          if (li < lj) {
+            if (olap >= li / 2) { fi &= ~1u; stop = true; }
+          } else if (lj < li) {
+            if (olap >= lj / 2) fj &= ~1u;
+          } else {
+            if (olap >= li / 2) {
+              fj |= 2u;
+              if (fi & 2u) { fi &= ~1u; stop = true; }
             }
           }
         }
+        wsync();
+        if (lane == 0) { flag[j] = (unsigned char)fj; flag[i] = (unsigned char)fi; if (changed) len[i] = li; }
+        wsync();
+        if (stop) break;
+        j0 = j + 1;                                    // rescan behind the candidate: the window may have grown
       }
-      for (int i = 0; i < n; i++)
-        if (flag[i] & 1) { s1[N] = s1[i]; s2[N] = s2[i]; len[N] = len[i]; rec[N] = rec[i]; N++; }
-      // ---- 2. union-find ----
-      for (int i = 0; i < N; i++) uf[i] = -1;
-      for (int i = 0; i < N - 1; i++) {
-        long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
-        for (int j = i + 1; j < N; j++) {
-          long long sep = (long long)s2[j] - i_end;
-          if (sep > P.maxgap) break;
-          long long dd = ll_abs(((long long)s2[j] - (long long)s1[j]) - i_diag);
-          long long lim = (long long)(P.diagfactor * (double)sep);
-          if (lim < P.diagdiff) lim = P.diagdiff;
-          if (dd <= lim) {
-            int a = uf_find(uf, i), c = uf_find(uf, j);
-            if (a != c) { if (a < c) uf[c] = a; else uf[a] = c; }
+    }
+    wsync();
+    // compaction of the surviving matches, in order
+    int N = 0;
+    for (int i0 = 0; i0 < n; i0 += MFSC_LANES) {
+      const int i = i0 + lane;
+      const bool keepm = i < n && (flag[i] & 1);
+      unsigned v1 = 0; int v2 = 0, v3 = 0, v4 = 0;
+      if (keepm) { v1 = s1[i]; v2 = s2[i]; v3 = len[i]; v4 = rec[i]; }
+      const unsigned m = wballot(keepm);
+      wsync();
+      if (keepm) {
+        const int w = N + dev_popc32(m & ((1u << lane) - 1u));
+        s1[w] = v1; s2[w] = v2; len[w] = v3; rec[w] = v4;
+      }
+      N += dev_popc32(m);
+      wsync();
+    }
+    // ---- 2. union-find ----
+    for (int i = lane; i < N; i += MFSC_LANES) uf[i] = -1;
+    wsync();
+    for (int i = 0; i < N - 1; i++) {
+      const long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
+      for (int j0 = i + 1; j0 < N; j0 += MFSC_LANES) {
+        const int jj = j0 + lane;
+        bool in = false, hit = false;
+        if (jj < N) {
+          const long long sep = (long long)s2[jj] - i_end;
+          in = sep <= P.maxgap;
+          if (in) {
+            const long long dd = ll_abs(((long long)s2[jj] - (long long)s1[jj]) - i_diag);
+            long long lim = (long long)(P.diagfactor * (double)sep);
+            if (lim < P.diagdiff) lim = P.diagdiff;
+            hit = dd <= lim;
           }
         }
+        unsigned m = wballot(hit);
+        if (m) {
+          if (lane == 0) {
+            while (m) {
+              const int j = j0 + dev_ffs32(m) - 1;
+              m &= m - 1u;
+              const int a = uf_find(uf, i), c = uf_find(uf, j);
+              if (a != c) { if (a < c) uf[c] = a; else uf[a] = c; }
+            }
+          }
+          wsync();
+        }
+        if (wballot(in) != all_lanes) break;
       }
+    }
+    wsync();
+    if (lane == 0) {
       // ---- 3. members grouped by component, components by smallest member ----
       for (int i = 0; i < N; i++) { from[i] = uf_find(uf, i); tmp[i] = 0; }   // from[] = root for now
       for (int i = 0; i < N; i++) tmp[from[i]]++;
@@ -109,7 +173,6 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
       for (int i = 0; i < N; i++) score[i] = from[i];
     }
     wsync();
-    N = wbcast_i32(N, 0);
     // ---- 4. chains ----
     int n_pc = 0, n_cm = 0;  // warp-uniform
     int c0 = 0;
