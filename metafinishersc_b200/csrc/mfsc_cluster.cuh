@@ -162,15 +162,19 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
       }
     }
     wsync();
+    // ---- 3. members grouped by component, components by smallest member ----
+    for (int i = lane; i < N; i += MFSC_LANES) {       // roots, read-only walk (no path compression while lanes share uf)
+      int r = i;
+      while (uf[r] >= 0) r = uf[r];
+      from[i] = r; score[i] = r; tmp[i] = 0;           // from[] = root for now; score[] keeps the roots
+    }
+    wsync();
     if (lane == 0) {
-      // ---- 3. members grouped by component, components by smallest member ----
-      for (int i = 0; i < N; i++) { from[i] = uf_find(uf, i); tmp[i] = 0; }   // from[] = root for now
       for (int i = 0; i < N; i++) tmp[from[i]]++;
       int acc = 0;
       for (int i = 0; i < N; i++) { int c = tmp[i]; tmp[i] = acc; acc += c; }    // tmp[root] = first slot
       for (int i = 0; i < N; i++) { ord[tmp[from[i]]++] = i; }
-      // after this, component with root r occupies ord[tmp[r]-count .. tmp[r]); score[] keeps the roots
-      for (int i = 0; i < N; i++) score[i] = from[i];
+      // after this, component with root r occupies ord[tmp[r]-count .. tmp[r])
     }
     wsync();
     // ---- 4. chains ----
