@@ -101,7 +101,7 @@ def test_engines_agree_on_substitution_errors(gpu_engine):
 
 
 def test_cfg5_scale_index(gpu_engine):
-    """BASELINE cfg 5 shape on the reference side: 100 contigs x 5 Mbp (500 Mbp index, k = 14), one read batch
+    """BASELINE cfg 5 shape on the reference side: 100 contigs x 5 Mbp (500 Mbp index, k = 15), one read batch
     drawn from known places.  Property: every read's longest row lands on its source contig and offset."""
     rng = np.random.default_rng(77)
     n_contigs, G, L, n_reads = 100, 5_000_000, 10_000, 4000
@@ -118,7 +118,7 @@ def test_cfg5_scale_index(gpu_engine):
     off = np.arange(n_contigs + 1, dtype=np.int64) * G
     ix = gpu_engine.index((buf, off), P)
     info = ix.info()
-    assert info["k"] == 14 and info["bases"] == n_contigs * G
+    assert info["k"] == 15 and info["bases"] == n_contigs * G
     r = gpu_engine.align(ix, reads, P)
     ix.free()
     best = {}
