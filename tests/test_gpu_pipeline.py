@@ -100,6 +100,40 @@ def test_engines_agree_on_substitution_errors(gpu_engine):
     assert out[0].stats["dp_retry_reads"] == 0 and len(out[0]) >= 1400
 
 
+@pytest.mark.parametrize("opts", [dict(breaklen=50), dict(minmatch=10), dict(band_cap=64), dict(simplify=False), dict(maxmatch=False),
+                                  dict(breaklen=20, band_cap=40)],
+                         ids=["b50", "l10", "cap64", "nosimplify", "mum", "b20cap40"])
+def test_engines_agree_under_options(gpu_engine, opts):
+    """Packed (with its small-rectangle path, whose size limit follows breaklen and band_cap) vs general engine under the
+    option sets the wrapper uses and a few extreme ones: both strands, accurate and noisy reads, reads with N runs."""
+    rng = np.random.default_rng(23)
+    d1 = datagen.abun_gap(G=400_000, repeat_len=3000, L=4000, p=0.01, abun=(3, 2), seed=5)
+    d2 = datagen.sc_lr(G=400_000, n_reads=150, seed=6, p_del=0.05, p_ins=0.05, L=5000)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    for i, r in enumerate(d1["reads"][:400] + d2["reads"]):
+        if i % 3 == 1:
+            r = r.translate(comp)[::-1]
+        if i % 11 == 0:
+            k = int(rng.integers(100, len(r) - 100))
+            r = r[:k] + b"N" * int(rng.integers(1, 30)) + r[k + 5:]
+        reads.append(r)
+    contigs = d1["contigs"] + d2["contigs"]
+    out = []
+    for eng in (0, 1):
+        P = engine.make_params(engine=eng, **opts)
+        ix = gpu_engine.index(contigs, P)
+        out.append(gpu_engine.align(ix, reads, P, flags=engine.WANT_DELTAS))
+        ix.free()
+    a, b = out
+    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for i in range(len(a)):        # the slices of the shared delta buffer are handed out in completion order: compare the lists
+        assert np.array_equal(a.deltas[a.delta_begin[i]:a.delta_end[i]], b.deltas[b.delta_begin[i]:b.delta_end[i]]), i
+    assert a.stats["cells"] == b.stats["cells"] and a.stats["dp_calls"] == b.stats["dp_calls"] and a.stats["max_band"] == b.stats["max_band"]
+    assert len(a) > 300 and a.stats["dp_retry_reads"] > 0          # the reads with N went through the general engine
+
+
 def test_cfg5_scale_index(gpu_engine):
     """BASELINE cfg 5 shape on the reference side: 100 contigs x 5 Mbp (500 Mbp index, k = 15), one read batch
     drawn from known places.  Property: every read's longest row lands on its source contig and offset."""
