@@ -45,6 +45,16 @@ def test_gpu_row_flags(gpu_engine):
     rowflag_cases.run(gpu_engine)
 
 
+@pytest.mark.parametrize("seed", range(60))
+def test_gpu_random_scenario(seed, gpu_engine, oracle):
+    """The seeded random scenarios of tests/test_emu_random.py (repeats, substitutions, indels, N runs, both strands, random
+    option sets, hand-over between the DP engines) through the C ABI on the GPU, bit-exact against the oracle."""
+    from tests import test_emu_random
+    contigs, reads, opts = test_emu_random.scenario(seed)
+    bad, r, o = cases.run_case(gpu_engine, oracle, contigs, reads, opts)
+    assert not bad, "seed %d %s: %s" % (seed, opts, "; ".join(bad))
+
+
 def test_gpu_determinism(gpu_engine):
     from metafinishersc_b200 import engine
     name, ref, qry, opts = CASES[1]
