@@ -169,13 +169,44 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
       from[i] = r; score[i] = r; tmp[i] = 0;           // from[] = root for now; score[] keeps the roots
     }
     wsync();
-    if (lane == 0) {
-      for (int i = 0; i < N; i++) tmp[from[i]]++;
-      int acc = 0;
-      for (int i = 0; i < N; i++) { int c = tmp[i]; tmp[i] = acc; acc += c; }    // tmp[root] = first slot
-      for (int i = 0; i < N; i++) { ord[tmp[from[i]]++] = i; }
-      // after this, component with root r occupies ord[tmp[r]-count .. tmp[r])
+    // stable counting sort of the members by root, 32 members at a time: lanes with the same root find each other
+    // with match.any, the lowest of them updates the root's counter, ranks inside the group follow lane order
+    const unsigned lt_mask = MFSC_LANES == 32 ? ((1u << lane) - 1u) : 0u;
+    for (int i0 = 0; i0 < N; i0 += MFSC_LANES) {
+      const int i = i0 + lane;
+      const int r = i < N ? from[i] : -1 - lane;
+      const unsigned m = wmatch_any_i32(r);
+      if (i < N && !(m & lt_mask)) tmp[r] += dev_popc32(m);
+      wsync();
     }
+    {
+      int acc = 0;                                                             // tmp[root] = first slot: exclusive scan
+      for (int i0 = 0; i0 < N; i0 += MFSC_LANES) {
+        const int i = i0 + lane;
+        const int c = i < N ? tmp[i] : 0;
+        int incl = c;
+#if MFSC_LANES == 32
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(MFSC_FULL, incl, o); if (lane >= o) incl += t; }
+#endif
+        if (i < N) tmp[i] = acc + incl - c;
+        acc += wbcast_i32(incl, MFSC_LANES - 1);
+      }
+    }
+    wsync();
+    for (int i0 = 0; i0 < N; i0 += MFSC_LANES) {
+      const int i = i0 + lane;
+      const int r = i < N ? from[i] : -1 - lane;
+      const unsigned m = wmatch_any_i32(r);
+      int base = 0;
+      if (i < N) base = tmp[r];
+      wsync();
+      if (i < N) {
+        ord[base + dev_popc32(m & lt_mask)] = i;
+        if (!(m & lt_mask)) tmp[r] = base + dev_popc32(m);
+      }
+      wsync();
+    }
+    // after this, component with root r occupies ord[tmp[r]-count .. tmp[r])
     wsync();
     // ---- 4. chains ----
     int n_pc = 0, n_cm = 0;  // warp-uniform
@@ -275,13 +306,19 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
           n_cm += wbcast_i32(add_cm, 0);
           n_pc += wbcast_i32(add_pc, 0);
         }
-        // remove the chain
+        // remove the chain: in-order compaction of the members left, 32 at a time
         int w = 0;
-        if (lane == 0) {
-          for (int i = 0; i < cn; i++) if (!flag[mem[i]]) mem[w++] = mem[i];
+        for (int i0 = 0; i0 < cn; i0 += MFSC_LANES) {
+          const int i = i0 + lane;
+          int v = 0; bool keepm = false;
+          if (i < cn) { v = mem[i]; keepm = !flag[v]; }
+          const unsigned m = wballot(keepm);
+          wsync();
+          if (keepm) mem[w + dev_popc32(m & lt_mask)] = v;
+          w += dev_popc32(m);
+          wsync();
         }
-        wsync();
-        cn = wbcast_i32(w, 0);
+        cn = w;
       }
       c0 = c1;
     }

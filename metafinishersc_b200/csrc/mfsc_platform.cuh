@@ -57,6 +57,7 @@ static inline long long wmin_i64(long long v) { return v; }
 static inline int wsum_i32(int v) { return v; }
 static inline long long wsum_i64(long long v) { return v; }
 static inline unsigned wballot(bool p) { return p ? 1u : 0u; }
+static inline unsigned wmatch_any_i32(int) { return 1u; }
 static inline int wbcast_i32(int v, int) { return v; }
 static inline long long wbcast_i64(long long v, int) { return v; }
 static inline unsigned atomic_add_u32(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
@@ -121,6 +122,7 @@ MFSC_DEV long long wsum_i64(long long v) {
   return v;
 }
 MFSC_DEV unsigned wballot(bool p) { return __ballot_sync(MFSC_FULL, p); }
+MFSC_DEV unsigned wmatch_any_i32(int v) { return __match_any_sync(MFSC_FULL, v); }   // lanes holding the same value
 MFSC_DEV int wbcast_i32(int v, int src) { return __shfl_sync(MFSC_FULL, v, src); }
 MFSC_DEV long long wbcast_i64(long long v, int src) { return __shfl_sync(MFSC_FULL, v, src); }
 MFSC_DEV unsigned atomic_add_u32(unsigned* p, unsigned v) { return atomicAdd(p, v); }
