@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""A longer run of the seeded random parity scenarios of tests/test_emu_random.py on the GPU (seeds 60..459): library through
+the C ABI against the oracle, rows-only and delta mode.  The test suite runs seeds 0..59."""
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import cases, test_emu_random
+from metafinishersc_b200 import engine
+from oracle import oracle as O
+O.build()
+E = engine.Engine()
+bad_total = 0
+for seed in range(60, 460):
+    contigs, reads, opts = test_emu_random.scenario(seed)
+    bad, r, o = cases.run_case(E, O, contigs, reads, opts)
+    if bad:
+        bad_total += 1
+        print("seed", seed, opts, bad[:2])
+print("sweep done, failures:", bad_total)
