@@ -55,6 +55,9 @@ const char* mfsc_last_error(void);
 int mfsc_version(void);
 int mfsc_device_count(int32_t* n);
 int mfsc_set_device(int32_t device);
+/* The library keeps one stream per calling thread (created by the thread's first call).  A worker thread that is about to
+ * end releases it with this call; the next call of the thread would create a new one. */
+int mfsc_thread_release(void);
 void mfsc_default_params(mfsc_params* p);
 
 /* pinned host memory for the buffers handed to the calls below (optional, speeds up the copies) */
@@ -68,15 +71,33 @@ int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec
 /* Replication over several GPUs: the root rank builds the index; every other rank creates an empty one of the
  * same shape (`build_tables` = 0, `p->kmer` and `n_positions` taken from the root's mfsc_index_info, `bases` may be
  * NULL), then all ranks fetch the device buffers with mfsc_index_buffers and broadcast them (NCCL through
- * torch.distributed, one call per buffer).  info: [0] k, [1] unused, [2] text words, [3] buckets+2, [4] positions,
+ * torch.distributed, one call per buffer).  info: [0] k, [1] device, [2] text words, [3] buckets+2, [4] positions,
  * [5] bytes in HBM, [6] records, [7] bases. */
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                       int32_t build_tables, int64_t n_positions, mfsc_index** out);
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]);
-/* ptr/bytes[4]: packed text, invalid mask, bucket heads, positions */
-int mfsc_index_buffers(const mfsc_index* ix, void* ptr[4], int64_t bytes[4]);
+/* ptr/bytes[5]: packed text, invalid mask, bucket heads, positions, bucket occupancy bitmap */
+int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]);
 int mfsc_index_build_ms(const mfsc_index* ix, double* ms);
 int mfsc_index_free(mfsc_index* ix);
+
+/* Index replication over the GPUs of one box (the reference's analogue is the fan-out of its 20 jobs over
+ * Pool(nProc) / MPI ranks, alignerRobot.py:114-166, each of which rebuilds the suffix tree of the whole reference): the
+ * index is built ONCE and every other GPU receives it with one ncclBroadcast per buffer over NVLink / NVSwitch.
+ *   one process, several GPUs (alignerRobot.useMummerAlignBatch with houseKeeper.globalGPUs > 1):
+ *     mfsc_comm_init_local(devices, n, &c);  ix[root] = the built index (it lives on devices[root]);
+ *     mfsc_index_broadcast(c, root, ix, &ms) creates ix[i] on devices[i] for every i != root and fills it.
+ *   one process per GPU (torchrun): rank 0 calls mfsc_comm_unique_id, the launcher ships the 128 bytes to the other ranks,
+ *     every rank calls mfsc_comm_init_rank after mfsc_set_device; mfsc_index_broadcast(c, root, &ix, &ms) with ix = the built
+ *     index on the root rank and NULL elsewhere (created there).
+ * NCCL is bound at run time (libnccl.so.2); without it these calls return MFSC_ERR_CUDA.  Replicas are freed with
+ * mfsc_index_free from any thread. */
+typedef struct mfsc_comm mfsc_comm;
+int mfsc_comm_unique_id(uint8_t id[128]);
+int mfsc_comm_init_rank(const uint8_t id[128], int32_t rank, int32_t world, mfsc_comm** out);
+int mfsc_comm_init_local(const int32_t* devices, int32_t n, mfsc_comm** out);
+int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms);
+int mfsc_comm_free(mfsc_comm* c);
 
 /* read batch upload (host -> HBM, packs both strands) */
 int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_reads, mfsc_reads** out);

@@ -11,7 +11,9 @@ a coords file keeps working.  `mummerLink` is accepted and ignored.  The contig 
 across calls, so the 20 read parts of one reads-vs-contigs alignment share one index instead of
 rebuilding it 20 times.  There is no CPU path: without the CUDA library every aligning call raises.
 """
+import hashlib
 import os
+import threading
 
 import numpy as np
 
@@ -19,10 +21,12 @@ from . import engine as _engine_mod
 from . import fasta, houseKeeper
 
 _ENGINE = None
-_INDEX_CACHE = {}      # (path, mtime_ns, size, minmatch) -> (Index, names, lens)
-_ROWS_CACHE = {}       # delta path -> RowSet
+_INDEX_CACHE = {}      # (content signature of the reference file, minmatch) -> (Index, names, lens)
+_ROWS_CACHE = {}       # delta path -> (RowSet, stat signature of the delta file this process wrote)
+_CACHE_LOCK = threading.RLock()     # the GPU fan-out (_batch_on_gpus) touches the caches from several host threads
 _INDEX_CACHE_MAX = 2
 _ROWS_CACHE_MAX = 64
+_HASH_WHOLE_BELOW = 64 << 20        # reference files up to this size are identified by a hash of all their bytes
 fullDelta = True       # write real MUMmer delta records (indel offset lists); False: alignment headers only, ~25 % faster
 
 
@@ -41,10 +45,57 @@ def get_engine():
 
 
 def clear_caches():
-    for ix, _, _ in _INDEX_CACHE.values():
-        ix.free()
-    _INDEX_CACHE.clear()
-    _ROWS_CACHE.clear()
+    with _CACHE_LOCK:
+        for ix, _, _ in _INDEX_CACHE.values():
+            ix.free()
+        _INDEX_CACHE.clear()
+        _ROWS_CACHE.clear()
+
+
+def _content_signature(path):
+    """Identifies the CONTENT of a reference file, not its path or time stamp: IORobot.alignWithName rewrites
+    `<name>leftSeg.fasta` in place on every call, usually with the same size, and a coarse mtime (1 s, NFS) would
+    make (path, mtime, size) collide.  Files up to 64 MB are hashed whole (a few ms); larger ones by size, inode,
+    ctime/mtime and a hash of their first and last MB."""
+    st = os.stat(path)
+    h = hashlib.blake2b(digest_size=16)
+    with open(path, "rb") as f:
+        if st.st_size <= _HASH_WHOLE_BELOW:
+            h.update(f.read())
+            return ("all", st.st_size, h.hexdigest())
+        h.update(f.read(1 << 20))
+        f.seek(st.st_size - (1 << 20))
+        h.update(f.read(1 << 20))
+    return ("ends", st.st_size, st.st_ino, st.st_ctime_ns, st.st_mtime_ns, h.hexdigest())
+
+
+def _stat_signature(path):
+    st = os.stat(path)
+    return (st.st_size, st.st_ino, st.st_mtime_ns, st.st_ctime_ns)
+
+
+def _rows_cache_put(delta, rs):
+    with _CACHE_LOCK:
+        while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX and delta not in _ROWS_CACHE:
+            _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)), None)
+        _ROWS_CACHE[delta] = (rs, _stat_signature(delta) if os.path.exists(delta) else None)
+
+
+def _rows_cache_get(delta):
+    """Rows this process produced for `delta`, as long as the file on disk is still the one it wrote."""
+    with _CACHE_LOCK:
+        hit = _ROWS_CACHE.get(delta)
+    if hit is None:
+        return None
+    rs, sig = hit
+    try:
+        if sig is not None and _stat_signature(delta) == sig:
+            return rs
+    except OSError:
+        pass
+    with _CACHE_LOCK:
+        _ROWS_CACHE.pop(delta, None)
+    return None
 
 
 class RowSet:
@@ -84,19 +135,19 @@ def _params(refinedVersion, maxmatch=True):
 
 
 def _get_index(E, ref_path, params):
-    st = os.stat(ref_path)
-    key = (os.path.abspath(ref_path), st.st_mtime_ns, st.st_size, params.minmatch)
-    hit = _INDEX_CACHE.get(key)
-    if hit is not None:
-        return hit
-    names, buf, off = fasta.read_fasta_arrays(ref_path)
-    names = [n.split()[0] if n.split() else n for n in names]      # nucmer ids stop at the first blank
-    while len(_INDEX_CACHE) >= _INDEX_CACHE_MAX:
-        old = next(iter(_INDEX_CACHE))
-        _INDEX_CACHE.pop(old)[0].free()
-    ix = E.index((buf, off), params)
-    _INDEX_CACHE[key] = (ix, names, np.diff(off).tolist())
-    return _INDEX_CACHE[key]
+    key = (_content_signature(ref_path), params.minmatch)
+    with _CACHE_LOCK:
+        hit = _INDEX_CACHE.get(key)
+        if hit is not None:
+            return hit
+        names, buf, off = fasta.read_fasta_arrays(ref_path)
+        names = [n.split()[0] if n.split() else n for n in names]      # nucmer ids stop at the first blank
+        while len(_INDEX_CACHE) >= _INDEX_CACHE_MAX:
+            old = next(iter(_INDEX_CACHE))
+            _INDEX_CACHE.pop(old)[0].free()
+        ix = E.index((buf, off), params)
+        _INDEX_CACHE[key] = (ix, names, np.diff(off).tolist())
+        return _INDEX_CACHE[key]
 
 
 def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
@@ -105,7 +156,8 @@ def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
     delta = prefix + ".delta"
     if not (os.path.exists(ref_path) and os.path.exists(qry_path)):
         print("ERROR: Could not find input file(s) %s %s" % (ref_path, qry_path))   # nucmer's failure is ignored upstream too
-        _ROWS_CACHE.pop(delta, None)
+        with _CACHE_LOCK:
+            _ROWS_CACHE.pop(delta, None)
         if os.path.exists(delta):
             os.remove(delta)
         return None
@@ -120,10 +172,8 @@ def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
         print("note: delta lists did not fit for %s, writing alignment headers only (%s)" % (qry_path, err))
         rows = E.align(ix, (qbuf, qoff), params)
     rs = RowSet(rows, rnames, rlens, qnames, np.diff(qoff).tolist(), ref_path, qry_path)
-    while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX:
-        _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)))
-    _ROWS_CACHE[delta] = rs
     E.write_delta(delta, rows, rnames, rlens, qnames, rs.qry_lens, os.path.abspath(ref_path), os.path.abspath(qry_path))
+    _rows_cache_put(delta, rs)
     return rs
 
 
@@ -176,7 +226,7 @@ def _load_delta(delta):
 
 
 def _rowset_for(delta):
-    rs = _ROWS_CACHE.get(delta)
+    rs = _rows_cache_get(delta)
     return rs if rs is not None else _load_delta(delta)
 
 
@@ -255,46 +305,64 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
 
 
 def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus):
-    """The reference's Pool(nProc) fan-out (alignerRobot.py:154-166) over the GPUs of one box: one host thread per
-    GPU (the C library keeps one device context and stream per thread), jobs dealt round-robin, every thread builds
-    the index of the references it meets on its own device.  Output files are the same as in the serial loop."""
-    import threading
+    """The reference's Pool(nProc) fan-out (alignerRobot.py:154-166) over the GPUs of one box: every distinct reference
+    of the batch is indexed ONCE (on the calling thread's device, through the index cache) and replicated to the other
+    GPUs with one NCCL broadcast per buffer (mfsc_index_broadcast); one host thread per GPU then takes the jobs
+    round-robin (the C library keeps one device context and stream per thread).  Output files are those of the serial loop."""
+    from . import multigpu
     main = get_engine()
     params = _params(refinedVersion)
     errors = []
+    replicas = {}                                # reference path -> ([Index per device], names, lens)
+    clique = None
+    try:
+        for job in workerList:
+            ref_path = folderName + job[1]
+            if ref_path in replicas or not os.path.exists(ref_path):
+                continue
+            ix, names, lens = _get_index(main, ref_path, params)
+            if clique is None:
+                root_dev = ix.info()["device"]
+                devices = [root_dev] + [d for d in range(n_gpus) if d != root_dev]
+                clique = multigpu.LocalClique(main, devices)
+            per_dev, _ = clique.broadcast(ix, root=0)
+            replicas[ref_path] = (per_dev, names, lens)
+        devices = clique.devices if clique is not None else list(range(n_gpus))
 
-    def work(dev):
-        try:
-            E = _engine_mod.Engine(main.L)
-            E.set_device(dev)
-            local = {}                       # reference path -> index entry on this device
-            for k in range(dev, len(workerList), n_gpus):
-                outputName, referenceName, queryName, specialName = workerList[k]
-                ref_path = folderName + referenceName
-                qry_path = queryName if specialForRaw else folderName + queryName
-                entry = None
-                if os.path.exists(ref_path):
-                    if ref_path not in local:
-                        names, buf, off = fasta.read_fasta_arrays(ref_path)
-                        names = [n.split()[0] if n.split() else n for n in names]
-                        local[ref_path] = (E.index((buf, off), params), names, np.diff(off).tolist())
-                    entry = local[ref_path]
-                rs = _run_nucmer(folderName + outputName, ref_path, qry_path, params, E=E, index_entry=entry)
-                out = folderName + (specialName if specialForRaw else outputName + "Out")
-                if rs is None:
-                    open(out, "w").close()
-                else:
-                    E.write_coords(out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=True)
-            for ix, _, _ in local.values():
+        def work(slot):
+            E = None
+            try:
+                E = _engine_mod.Engine(main.L)
+                E.set_device(devices[slot])
+                for k in range(slot, len(workerList), n_gpus):
+                    outputName, referenceName, queryName, specialName = workerList[k]
+                    ref_path = folderName + referenceName
+                    qry_path = queryName if specialForRaw else folderName + queryName
+                    rep = replicas.get(ref_path)
+                    entry = (rep[0][slot], rep[1], rep[2]) if rep is not None else None
+                    rs = _run_nucmer(folderName + outputName, ref_path, qry_path, params, E=E, index_entry=entry)
+                    out = folderName + (specialName if specialForRaw else outputName + "Out")
+                    if rs is None:
+                        open(out, "w").close()
+                    else:
+                        E.write_coords(out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=True)
+            except Exception as e:       # surfaced in the caller's thread
+                errors.append(e)
+            finally:
+                if E is not None:
+                    E.thread_release()   # the worker's stream goes with the worker
+
+        threads = [threading.Thread(target=work, args=(d,)) for d in range(n_gpus)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        for per_dev, _, _ in replicas.values():
+            for ix in per_dev[1:]:               # entry 0 is the cached index of the calling thread
                 ix.free()
-        except Exception as e:       # surfaced in the caller's thread
-            errors.append(e)
-
-    threads = [threading.Thread(target=work, args=(d,)) for d in range(n_gpus)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+        if clique is not None:
+            clique.free()
     if errors:
         raise errors[0]
 
@@ -338,7 +406,7 @@ def largeRvsQAlign(folderName, numberOfFiles, mummerLink, refFile, qryFile, mumT
     useMummerAlignBatch(mummerLink, folderName, workerList, houseKeeper.globalParallel, False)
     dataList = []
     for i in range(1, numberOfFiles + 1):
-        rs = _ROWS_CACHE.get(folderName + mumTmpHeader + zeropadding(i) + ".delta")
+        rs = _rows_cache_get(folderName + mumTmpHeader + zeropadding(i) + ".delta")
         # rows served from memory when this process produced them; identical to parsing the text
         dataList = dataList + (rs.datalist() if rs is not None else extractMumData(folderName, mumTmpHeader + zeropadding(i) + "Out"))
     return dataList

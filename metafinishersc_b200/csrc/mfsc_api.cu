@@ -30,8 +30,9 @@ namespace {
 
 #ifdef MFSC_EMU
 struct Dev {
-  cudaStream_t stream = 0;
+  cudaStream_t stream = 1;
   long long launches = 0;
+  int device = 0;
   bool ok() { return true; }
   void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
   void free_(void* p) { free(p); }
@@ -51,12 +52,14 @@ struct Dev {
   cudaStream_t stream = 0;
   long long launches = 0;
   int sm = 0;
+  int device = -1;
   bool ok() {
     if (stream) return true;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return false; }
     if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
     int d = 0; cudaGetDevice(&d);
+    device = d;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, d);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
@@ -89,6 +92,23 @@ static void stamp_free(Stamp& s) { if (s.e) cudaEventDestroy(s.e); s.e = nullptr
 #endif
 
 static thread_local Dev g_dev;
+
+#ifdef MFSC_EMU
+struct DeviceGuard { explicit DeviceGuard(int) {} };
+static void dev_free_plain(void* p) { free(p); }
+#else
+// switches to a device for the lifetime of the object (frees and copies that concern another device than the thread's own)
+struct DeviceGuard {
+  int prev = -1; bool sw = false;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; return; }
+    if (prev != dev) { sw = cudaSetDevice(dev) == cudaSuccess; if (!sw) cudaGetLastError(); }
+  }
+  ~DeviceGuard() { if (sw && prev >= 0) cudaSetDevice(prev); }
+};
+static void dev_free_plain(void* p) { if (p && cudaFree(p) != cudaSuccess) cudaGetLastError(); }   // also valid for stream-ordered allocations (synchronises)
+#endif
 
 template <class T> T* dalloc(Dev& D, size_t n) { return (T*)D.alloc(n * sizeof(T)); }
 
@@ -273,12 +293,18 @@ struct mfsc_index {
   unsigned* ostart = nullptr;   // separator-joined coordinate of each record
   std::vector<unsigned> h_ostart;
   unsigned* H = nullptr; unsigned* pos = nullptr;
+  unsigned* occ = nullptr;      // one bit per bucket: not empty
   int k = 0; long long n_buckets = 0, n_pos = 0;
   double build_ms = 0;
+  int device = -1;              // device the buffers live on
+  bool plain = false;           // buffers come from cudaMalloc (replicas made by mfsc_index_broadcast), not from the stream-ordered pool
 };
 
 struct mfsc_reads {
   SeqDev q;
+  unsigned* tile_off = nullptr;   // [n_seq + 1] first seed tile of every strand (mfsc_seed.cuh)
+  unsigned n_tiles = 0;
+  int device = -1;
   int n_reads = 0;
   double upload_ms = 0;
   long long h2d_bytes = 0;
@@ -327,6 +353,14 @@ int mfsc_set_device(int32_t device) {
 #endif
 }
 
+int mfsc_thread_release(void) {
+#ifndef MFSC_EMU
+  Dev& D = g_dev;
+  if (D.stream) { cudaStreamSynchronize(D.stream); cudaStreamDestroy(D.stream); D.stream = 0; D.device = -1; }
+#endif
+  return MFSC_OK;
+}
+
 void mfsc_default_params(mfsc_params* p) {
   memset(p, 0, sizeof(*p));
   p->minmatch = 20; p->mincluster = 65; p->maxgap = 90; p->breaklen = 200; p->diagdiff = 5; p->maxmatch = 1; p->simplify = 1;
@@ -373,6 +407,21 @@ static int choose_k(const mfsc_params* p, long long n_bases) {
   return k;
 }
 
+// every failure path releases what it had allocated
+static void index_release(Dev& D, mfsc_index* ix) {
+  if (!ix) return;
+  if (ix->plain || !D.stream || (ix->device >= 0 && ix->device != D.device)) {
+    // buffers of another device (or of a replica made with cudaMalloc): free them synchronously on their own device
+    DeviceGuard g(ix->device);
+    dev_free_plain(ix->ref.txt); dev_free_plain(ix->ref.inv); dev_free_plain(ix->ref.start); dev_free_plain(ix->ref.len);
+    dev_free_plain(ix->ostart); dev_free_plain(ix->H); dev_free_plain(ix->pos); dev_free_plain(ix->occ);
+  } else {
+    seq_free(D, ix->ref);
+    D.free_(ix->ostart); D.free_(ix->H); D.free_(ix->pos); D.free_(ix->occ);
+  }
+  delete ix;
+}
+
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p, int32_t build_tables,
                       int64_t n_positions, mfsc_index** out) {
   if (!rec_off || n_rec <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_index_create: bad arguments");
@@ -381,41 +430,44 @@ int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_re
   Dev& D = g_dev;
   if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
   mfsc_index* ix = new mfsc_index();
+  ix->device = D.device;
   std::string err;
   Stamp t0, t1;
   stamp(D, t0);
-  if (!seq_upload(D, bases, rec_off, n_rec, 0, build_tables != 0, ix->ref, err)) { delete ix; return fail(MFSC_ERR_NOMEM, err); }
+  if (!seq_upload(D, bases, rec_off, n_rec, 0, build_tables != 0, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
   ix->h_ostart.resize(n_rec);
   for (int r = 0; r < n_rec; r++) ix->h_ostart[r] = (unsigned)(rec_off[r] - rec_off[0] + r);
   ix->ostart = dalloc<unsigned>(D, n_rec);
-  D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
   ix->k = choose_k(p, ix->ref.n_bases);
   ix->n_buckets = 1ll << (2 * ix->k);
   ix->H = dalloc<unsigned>(D, ix->n_buckets + 2);
-  if (!ix->H || !ix->ostart) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (bucket table)"); }
+  ix->occ = dalloc<unsigned>(D, ix->n_buckets / 32 + 2);
+  if (!ix->H || !ix->ostart || !ix->occ) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (bucket table)"); }
+  D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
   if (build_tables) {
     D.zero(ix->H, sizeof(unsigned) * (ix->n_buckets + 2));
     const unsigned g = grid_for(D, ix->ref.n_words, 256, 16);
     MFSC_LAUNCH(k_index_count, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H);
-    if (!inclusive_sum_u32(D, ix->H, ix->n_buckets + 2)) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
+    if (!inclusive_sum_u32(D, ix->H, ix->n_buckets + 2)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
     unsigned total = 0;
     D.d2h(&total, ix->H + ix->n_buckets + 1, sizeof(unsigned));
     ix->n_pos = total;
     ix->pos = dalloc<unsigned>(D, (size_t)total + 1);
-    if (!ix->pos) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
+    if (!ix->pos) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
     MFSC_LAUNCH(k_index_fill, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H, ix->pos);
-    D.launches += 2;
+    MFSC_LAUNCH(k_index_occ, grid_for(D, ix->n_buckets / 32 + 1, 256, 16), 256, 0, D.stream, ix->H, ix->n_buckets, ix->occ);
+    D.launches += 3;
   } else {
     ix->n_pos = n_positions;
     ix->pos = dalloc<unsigned>(D, (size_t)n_positions + 1);
-    if (!ix->pos) { delete ix; return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
+    if (!ix->pos) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
   }
   stamp(D, t1);
   D.sync();
   ix->build_ms = elapsed_ms(D, t0, t1);
   stamp_free(t0); stamp_free(t1);
   std::string msg;
-  if (!dev_check(msg)) { return fail(MFSC_ERR_CUDA, "index build: " + msg); }
+  if (!dev_check(msg)) { index_release(D, ix); return fail(MFSC_ERR_CUDA, "index build: " + msg); }
   *out = ix;
   return MFSC_OK;
 }
@@ -426,18 +478,19 @@ int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec
 
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]) {
   if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
-  info[0] = ix->k; info[1] = 0; info[2] = ix->ref.n_words; info[3] = ix->n_buckets + 2; info[4] = ix->n_pos;
-  info[5] = (int64_t)ix->ref.n_words * 12 + (ix->n_buckets + 2) * 4 + (ix->n_pos + 1) * 4;
+  info[0] = ix->k; info[1] = ix->device; info[2] = ix->ref.n_words; info[3] = ix->n_buckets + 2; info[4] = ix->n_pos;
+  info[5] = (int64_t)ix->ref.n_words * 12 + (ix->n_buckets + 2) * 4 + (ix->n_pos + 1) * 4 + (ix->n_buckets / 32 + 2) * 4;
   info[6] = ix->ref.n_seq; info[7] = ix->ref.n_bases;
   return MFSC_OK;
 }
 
-int mfsc_index_buffers(const mfsc_index* ix, void* ptr[4], int64_t bytes[4]) {
+int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]) {
   if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
   ptr[0] = ix->ref.txt; bytes[0] = (int64_t)ix->ref.n_words * 8;
   ptr[1] = ix->ref.inv; bytes[1] = (int64_t)ix->ref.n_words * 4;
   ptr[2] = ix->H; bytes[2] = (ix->n_buckets + 2) * 4;
   ptr[3] = ix->pos; bytes[3] = (ix->n_pos + 1) * 4;
+  ptr[4] = ix->occ; bytes[4] = (ix->n_buckets / 32 + 2) * 4;
   return MFSC_OK;
 }
 
@@ -445,11 +498,271 @@ int mfsc_index_build_ms(const mfsc_index* ix, double* ms) { if (!ix) return fail
 
 int mfsc_index_free(mfsc_index* ix) {
   if (!ix) return MFSC_OK;
-  Dev& D = g_dev;
-  seq_free(D, ix->ref);
-  D.free_(ix->ostart); D.free_(ix->H); D.free_(ix->pos);
-  delete ix;
+  index_release(g_dev, ix);
   return MFSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// index replication over the GPUs of one box: one NCCL broadcast per index buffer over NVLink.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy torch has already loaded in a torchrun rank, the
+// system one otherwise), so the library itself loads on a machine without it; the calls below then fail loudly.
+// ------------------------------------------------------------------------------------------
+#ifndef MFSC_EMU
+}  // extern "C"
+#include <dlfcn.h>
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_uid { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+  int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("NCCL not found: ") + dlerror(); return false; }
+#define MFSC_NCCL_SYM(field, sym) field = (decltype(field))dlsym(lib, sym); if (!field) { err = std::string("NCCL symbol missing: ") + sym; lib = nullptr; return false; }
+    MFSC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") MFSC_NCCL_SYM(CommInitRank, "ncclCommInitRank") MFSC_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    MFSC_NCCL_SYM(CommDestroy, "ncclCommDestroy") MFSC_NCCL_SYM(Broadcast, "ncclBroadcast") MFSC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    MFSC_NCCL_SYM(GroupEnd, "ncclGroupEnd") MFSC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef MFSC_NCCL_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+const int NCCL_U8 = 1;   // ncclUint8
+}  // namespace
+extern "C" {
+#endif
+
+struct mfsc_comm {
+  int world = 0, rank = -1;          // rank >= 0: one process per GPU; rank < 0: one process, `world` devices
+  std::vector<int> devices;          // local clique: device of every member
+#ifndef MFSC_EMU
+  std::vector<nccl_comm_t> comms;    // local clique: one per device; ranks: one
+  std::vector<cudaStream_t> streams;
+#endif
+};
+
+int mfsc_comm_unique_id(uint8_t id[128]) {
+#ifdef MFSC_EMU
+  memset(id, 0, 128); return MFSC_OK;
+#else
+  if (!id) return fail(MFSC_ERR_ARG, "mfsc_comm_unique_id: id is NULL");
+  if (!g_nccl.load()) return fail(MFSC_ERR_CUDA, g_nccl.err);
+  nccl_uid u;
+  int rc = g_nccl.GetUniqueId(&u);
+  if (rc) return fail(MFSC_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+  memcpy(id, u.internal, 128);
+  return MFSC_OK;
+#endif
+}
+
+int mfsc_comm_init_rank(const uint8_t id[128], int32_t rank, int32_t world, mfsc_comm** out) {
+  if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(MFSC_ERR_ARG, "mfsc_comm_init_rank: bad arguments");
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  mfsc_comm* c = new mfsc_comm();
+  c->world = world; c->rank = rank; c->devices.push_back(D.device);
+#ifndef MFSC_EMU
+  if (!g_nccl.load()) { delete c; return fail(MFSC_ERR_CUDA, g_nccl.err); }
+  nccl_uid u; memcpy(u.internal, id, 128);
+  nccl_comm_t nc = nullptr;
+  int rc = g_nccl.CommInitRank(&nc, world, u, rank);
+  if (rc) { delete c; return fail(MFSC_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); }
+  c->comms.push_back(nc); c->streams.push_back(D.stream);
+#endif
+  *out = c;
+  return MFSC_OK;
+}
+
+int mfsc_comm_init_local(const int32_t* devices, int32_t n, mfsc_comm** out) {
+  if (!devices || n < 1 || !out) return fail(MFSC_ERR_ARG, "mfsc_comm_init_local: bad arguments");
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  mfsc_comm* c = new mfsc_comm();
+  c->world = n; c->rank = -1; c->devices.assign(devices, devices + n);
+#ifndef MFSC_EMU
+  if (!g_nccl.load()) { delete c; return fail(MFSC_ERR_CUDA, g_nccl.err); }
+  c->comms.resize(n); c->streams.resize(n);
+  std::vector<int> devs(devices, devices + n);
+  int rc = g_nccl.CommInitAll(c->comms.data(), n, devs.data());
+  if (rc) { delete c; return fail(MFSC_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(rc)); }
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(devs[i]);
+    if (cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete c; return fail(MFSC_ERR_CUDA, "cudaStreamCreate failed"); }
+  }
+#endif
+  *out = c;
+  return MFSC_OK;
+}
+
+int mfsc_comm_free(mfsc_comm* c) {
+  if (!c) return MFSC_OK;
+#ifndef MFSC_EMU
+  for (size_t i = 0; i < c->comms.size(); i++) if (c->comms[i]) g_nccl.CommDestroy(c->comms[i]);
+  if (c->rank < 0) for (size_t i = 0; i < c->streams.size(); i++) { DeviceGuard g(c->devices[i]); if (c->streams[i]) cudaStreamDestroy(c->streams[i]); }
+#endif
+  delete c;
+  return MFSC_OK;
+}
+
+#ifndef MFSC_EMU
+// an index of the root's shape on `device`, buffers from cudaMalloc, contents to be received
+static mfsc_index* index_shell(int device, int k, unsigned n_words, long long n_pos, const std::vector<unsigned>& h_start,
+                               const std::vector<int>& h_len, const std::vector<unsigned>& h_ostart, long long n_bases) {
+  DeviceGuard g(device);
+  mfsc_index* ix = new mfsc_index();
+  ix->device = device; ix->plain = true;
+  ix->k = k; ix->n_buckets = 1ll << (2 * k); ix->n_pos = n_pos;
+  ix->ref.n_seq = (int)h_len.size(); ix->ref.n_words = n_words; ix->ref.n_bases = n_bases;
+  ix->ref.h_start = h_start; ix->ref.h_len = h_len; ix->h_ostart = h_ostart;
+  const size_t ns = h_len.size();
+  bool ok = cudaMalloc(&ix->ref.txt, sizeof(unsigned long long) * (size_t)n_words) == cudaSuccess &&
+            cudaMalloc(&ix->ref.inv, sizeof(unsigned) * (size_t)n_words) == cudaSuccess &&
+            cudaMalloc(&ix->ref.start, sizeof(unsigned) * (ns + 1)) == cudaSuccess &&
+            cudaMalloc(&ix->ref.len, sizeof(int) * (ns + 1)) == cudaSuccess &&
+            cudaMalloc(&ix->ostart, sizeof(unsigned) * (ns + 1)) == cudaSuccess &&
+            cudaMalloc(&ix->H, sizeof(unsigned) * (size_t)(ix->n_buckets + 2)) == cudaSuccess &&
+            cudaMalloc(&ix->pos, sizeof(unsigned) * (size_t)(n_pos + 1)) == cudaSuccess &&
+            cudaMalloc(&ix->occ, sizeof(unsigned) * (size_t)(ix->n_buckets / 32 + 2)) == cudaSuccess;
+  if (ok) ok = cudaMemcpy(ix->ref.start, h_start.data(), sizeof(unsigned) * ns, cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(ix->ref.len, h_len.data(), sizeof(int) * ns, cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(ix->ostart, h_ostart.data(), sizeof(unsigned) * ns, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); Dev none; none.stream = 0; index_release(none, ix); return nullptr; }
+  return ix;
+}
+#endif
+
+int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms) {
+  if (!c || !ix || root < 0 || root >= c->world) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: bad arguments");
+  if (ms) *ms = 0;
+#ifdef MFSC_EMU
+  // host emulation (tests only): "devices" are the one host; replicas are plain copies
+  if (c->rank >= 0) return ix[0] ? MFSC_OK : fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the host emulation has one rank");
+  const mfsc_index* r = ix[root];
+  if (!r) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the root index is NULL");
+  for (int i = 0; i < c->world; i++) {
+    if (i == root) continue;
+    mfsc_index* n = new mfsc_index(*r);
+    auto dup = [](const void* src, size_t bytes) { void* d = calloc(bytes ? bytes : 1, 1); memcpy(d, src, bytes); return d; };
+    const size_t ns = (size_t)r->ref.n_seq;
+    n->ref.txt = (unsigned long long*)dup(r->ref.txt, 8 * (size_t)r->ref.n_words); n->ref.inv = (unsigned*)dup(r->ref.inv, 4 * (size_t)r->ref.n_words);
+    n->ref.start = (unsigned*)dup(r->ref.start, 4 * ns); n->ref.len = (int*)dup(r->ref.len, 4 * ns); n->ostart = (unsigned*)dup(r->ostart, 4 * ns);
+    n->H = (unsigned*)dup(r->H, 4 * (size_t)(r->n_buckets + 2)); n->pos = (unsigned*)dup(r->pos, 4 * (size_t)(r->n_pos + 1));
+    n->occ = (unsigned*)dup(r->occ, 4 * (size_t)(r->n_buckets / 32 + 2));
+    ix[i] = n;
+  }
+  return MFSC_OK;
+#else
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  const auto t0 = std::chrono::steady_clock::now();
+  auto bcast = [&](std::vector<void*>& send_recv, size_t bytes) -> int {
+    // one ncclBroadcast per member of this process, grouped
+    int rc = g_nccl.GroupStart();
+    for (size_t i = 0; i < c->comms.size() && !rc; i++) {
+      const int member = c->rank >= 0 ? c->rank : (int)i;
+      (void)member;
+      rc = g_nccl.Broadcast(send_recv[i], send_recv[i], bytes, NCCL_U8, root, c->comms[i], c->streams[i]);
+    }
+    int rc2 = g_nccl.GroupEnd();
+    return rc ? rc : rc2;
+  };
+  auto sync_all = [&]() {
+    for (size_t i = 0; i < c->streams.size(); i++) { DeviceGuard g(c->devices[i]); cudaStreamSynchronize(c->streams[i]); }
+  };
+  if (c->rank < 0) {
+    // ---- one process: ix[root] is built, ix[i] is created on devices[i] ----
+    mfsc_index* r = ix[root];
+    if (!r || r->device != c->devices[root]) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the root index does not live on devices[root]");
+    for (int i = 0; i < c->world; i++) {
+      if (i == root) continue;
+      ix[i] = index_shell(c->devices[i], r->k, r->ref.n_words, r->n_pos, r->ref.h_start, r->ref.h_len, r->h_ostart, r->ref.n_bases);
+      if (!ix[i]) { for (int j = 0; j < i; j++) if (j != root) { mfsc_index_free(ix[j]); ix[j] = nullptr; } return fail(MFSC_ERR_NOMEM, "out of device memory (index replica)"); }
+    }
+    void* rp[5]; int64_t rb[5];
+    mfsc_index_buffers(r, rp, rb);
+    for (int b = 0; b < 5; b++) {
+      std::vector<void*> bufs(c->world);
+      for (int i = 0; i < c->world; i++) { void* p[5]; int64_t nb[5]; mfsc_index_buffers(ix[i], p, nb); bufs[i] = p[b]; }
+      int rc = bcast(bufs, (size_t)rb[b]);
+      if (rc) return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(rc));
+    }
+    sync_all();
+  } else {
+    // ---- one process per GPU: shape first, then the record tables, then the five buffers ----
+    long long meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    mfsc_index* r = ix[0];
+    if (c->rank == root) {
+      if (!r) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the root rank has no index");
+      meta[0] = r->k; meta[1] = r->ref.n_words; meta[2] = r->n_pos; meta[3] = r->ref.n_seq; meta[4] = r->ref.n_bases;
+    }
+    long long* d_meta = dalloc<long long>(D, 8);
+    if (!d_meta) return fail(MFSC_ERR_NOMEM, "out of device memory (broadcast)");
+    D.h2d(d_meta, meta, sizeof(meta)); D.sync();
+    std::vector<void*> one(1);
+    one[0] = d_meta;
+    int rc = bcast(one, sizeof(meta));
+    if (rc) { D.free_(d_meta); return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(rc)); }
+    D.d2h(meta, d_meta, sizeof(meta));
+    D.free_(d_meta);
+    const size_t ns = (size_t)meta[3];
+    std::vector<unsigned> tab(3 * ns + 1);
+    if (c->rank == root) {
+      memcpy(tab.data(), r->ref.h_start.data(), 4 * ns); memcpy(tab.data() + ns, r->ref.h_len.data(), 4 * ns);
+      memcpy(tab.data() + 2 * ns, r->h_ostart.data(), 4 * ns);
+    }
+    unsigned* d_tab = dalloc<unsigned>(D, 3 * ns + 1);
+    if (!d_tab) return fail(MFSC_ERR_NOMEM, "out of device memory (broadcast)");
+    D.h2d(d_tab, tab.data(), 4 * 3 * ns); D.sync();
+    one[0] = d_tab;
+    rc = bcast(one, 4 * 3 * ns);
+    if (rc) { D.free_(d_tab); return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(rc)); }
+    D.d2h(tab.data(), d_tab, 4 * 3 * ns);
+    D.free_(d_tab);
+    if (c->rank != root) {
+      std::vector<unsigned> hs(tab.begin(), tab.begin() + ns), ho(tab.begin() + 2 * ns, tab.begin() + 3 * ns);
+      std::vector<int> hl(ns);
+      memcpy(hl.data(), tab.data() + ns, 4 * ns);
+      r = index_shell(D.device, (int)meta[0], (unsigned)meta[1], meta[2], hs, hl, ho, meta[4]);
+      if (!r) return fail(MFSC_ERR_NOMEM, "out of device memory (index replica)");
+      ix[0] = r;
+    }
+    void* p[5]; int64_t nb[5];
+    mfsc_index_buffers(r, p, nb);
+    for (int b = 0; b < 5; b++) {
+      one[0] = p[b];
+      rc = bcast(one, (size_t)nb[b]);
+      if (rc) return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(rc));
+    }
+    D.sync();
+  }
+  if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::string msg;
+  if (!dev_check(msg)) return fail(MFSC_ERR_CUDA, "index broadcast: " + msg);
+  return MFSC_OK;
+#endif
+}
+
+static void reads_release(Dev& D, mfsc_reads* r) {
+  if (!r) return;
+  if (!D.stream || (r->device >= 0 && r->device != D.device)) {
+    DeviceGuard g(r->device);
+    dev_free_plain(r->q.txt); dev_free_plain(r->q.inv); dev_free_plain(r->q.start); dev_free_plain(r->q.len); dev_free_plain(r->tile_off);
+  } else {
+    seq_free(D, r->q);
+    D.free_(r->tile_off);
+  }
+  delete r;
 }
 
 int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_reads, mfsc_reads** out) {
@@ -457,26 +770,37 @@ int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_r
   Dev& D = g_dev;
   if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
   mfsc_reads* r = new mfsc_reads();
+  r->device = D.device;
   std::string err;
   Stamp t0, t1;
   stamp(D, t0);
-  if (!seq_upload(D, bases, read_off, n_reads, 1, true, r->q, err)) { delete r; return fail(MFSC_ERR_NOMEM, err); }
+  if (!seq_upload(D, bases, read_off, n_reads, 1, true, r->q, err)) { reads_release(D, r); return fail(MFSC_ERR_NOMEM, err); }
+  // seed tiles: a strand of len bases is probed in tiles of SEED_TILE_BASES bases (mfsc_seed.cuh)
+  {
+    std::vector<unsigned> toff(r->q.n_seq + 1);
+    unsigned long long acc = 0;
+    for (int k = 0; k < r->q.n_seq; k++) { toff[k] = (unsigned)acc; acc += (unsigned long long)((r->q.h_len[k] + SEED_TILE_BASES - 1) / SEED_TILE_BASES); }
+    toff[r->q.n_seq] = (unsigned)acc;
+    r->n_tiles = (unsigned)acc;
+    r->tile_off = dalloc<unsigned>(D, r->q.n_seq + 1);
+    if (!r->tile_off) { reads_release(D, r); return fail(MFSC_ERR_NOMEM, "out of device memory (seed tiles)"); }
+    D.h2d(r->tile_off, toff.data(), sizeof(unsigned) * (r->q.n_seq + 1));
+    D.sync();
+  }
   stamp(D, t1);
   D.sync();
   r->upload_ms = elapsed_ms(D, t0, t1);
   stamp_free(t0); stamp_free(t1);
   r->n_reads = n_reads;
-  r->h2d_bytes = r->q.n_bases + (long long)sizeof(long long) * (n_reads + 1) + 12ll * r->q.n_seq;
+  r->h2d_bytes = r->q.n_bases + (long long)sizeof(long long) * (n_reads + 1) + 12ll * r->q.n_seq + 4ll * (r->q.n_seq + 1);
   std::string msg;
-  if (!dev_check(msg)) { return fail(MFSC_ERR_CUDA, "reads upload: " + msg); }
+  if (!dev_check(msg)) { reads_release(D, r); return fail(MFSC_ERR_CUDA, "reads upload: " + msg); }
   *out = r;
   return MFSC_OK;
 }
 
 int mfsc_reads_free(mfsc_reads* r) {
-  if (!r) return MFSC_OK;
-  seq_free(g_dev, r->q);
-  delete r;
+  reads_release(g_dev, r);
   return MFSC_OK;
 }
 
@@ -507,37 +831,38 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
   stamp(D, ts[0]);
 
   // ---- stage 2: probes -> maximal exact matches ----
-  std::vector<ProbeChunk> chunks;
   long long n_probes = 0;
-  const int CH = 2048;
   for (int qs = 0; qs < n_qs; qs++) {
     int len = rd->q.h_len[qs];
-    int np = len >= P.k ? (len - P.k) / P.stride + 1 : 0;
-    n_probes += np;
-    for (int b = 0; b < np; b += CH) { ProbeChunk c; c.qs = qs; c.pb = b; c.pe = std::min(np, b + CH); chunks.push_back(c); }
+    n_probes += len >= P.k ? (len - P.k) / P.stride + 1 : 0;
   }
-  DA(ProbeChunk, d_chunks, chunks.size());
-  D.h2d(d_chunks, chunks.data(), sizeof(ProbeChunk) * chunks.size());
   DA(unsigned, d_counter, 8);
   long long cap = std::max<long long>(1 << 16, rd->q.n_bases / 16);
   MemOut mo; unsigned found = 0;
   int *m_qs = nullptr, *m_s2 = nullptr, *m_len = nullptr, *m_rec = nullptr; unsigned* m_s1 = nullptr;
+  SeedTiles ST; ST.tile_off = rd->tile_off; ST.n_tiles = rd->n_tiles; ST.ticket = d_counter + 4;
   for (int attempt = 0; attempt < 3; attempt++) {
     m_qs = (int*)D.alloc(sizeof(int) * (cap + 1)); m_s1 = (unsigned*)D.alloc(sizeof(unsigned) * (cap + 1));
     m_s2 = (int*)D.alloc(sizeof(int) * (cap + 1)); m_len = (int*)D.alloc(sizeof(int) * (cap + 1)); m_rec = (int*)D.alloc(sizeof(int) * (cap + 1));
-    if (!m_qs || !m_s1 || !m_s2 || !m_len || !m_rec) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (matches)"); }
+    if (!m_qs || !m_s1 || !m_s2 || !m_len || !m_rec) {
+      D.free_(m_qs); D.free_(m_s1); D.free_(m_s2); D.free_(m_len); D.free_(m_rec);
+      cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (matches)");
+    }
     D.zero(d_counter, sizeof(unsigned) * 8);
     mo.qs = m_qs; mo.s1 = m_s1; mo.s2 = m_s2; mo.len = m_len; mo.rec = m_rec; mo.counter = d_counter; mo.capacity = (unsigned)cap;
-    if (!chunks.empty()) {
-      MFSC_LAUNCH(k_seeds, grid_for(D, (long long)chunks.size() * 128, 128, 16), 128, 0, D.stream, RS, ix->ostart, ix->H, ix->pos, QS, d_chunks,
-                  (int)chunks.size(), P, mo);
+    if (rd->n_tiles > 0) {
+      // persistent grid: warps take tiles of the query strands from a ticket counter
+      MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, 8), MFSC_LANES * SEED_WARPS, 0, D.stream,
+                  RS, ix->ostart, ix->H, ix->pos, ix->occ, QS, ST, P, mo);
       D.launches++;
     }
     D.d2h(&found, d_counter, sizeof(unsigned));
     if ((long long)found <= cap) break;
     D.free_(m_qs); D.free_(m_s1); D.free_(m_s2); D.free_(m_len); D.free_(m_rec);
+    m_qs = m_s2 = m_len = m_rec = nullptr; m_s1 = nullptr;
     cap = (long long)found + 1024;
   }
+  if (!m_qs) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "match buffer: the retry did not converge"); }
   keep(m_qs); keep(m_s1); keep(m_s2); keep(m_len); keep(m_rec);
   if ((unsigned long long)found >= 0x7fffffffull) { cleanup(); delete res; return fail(MFSC_ERR_ARG, "more than 2^31 matches in one batch: split the reads into smaller batches"); }
   const long long M = found;
@@ -587,7 +912,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     W.s1 = w_s1; W.s2 = w_s2; W.len = w_len; W.rec = w_rec; W.score = w_score; W.adj = w_adj; W.from = w_from; W.uf = w_uf;
     W.ord = w_ord; W.tmp = w_tmp; W.flag = w_flag;
     O.s1 = o_s1; O.s2 = o_s2; O.len = o_len; O.pc_first = o_pcf; O.pc_n = o_pcn; O.pc_rec = o_pcr; O.n_pc = o_npc; O.n_cm = o_ncm;
-    MFSC_LAUNCH(k_cluster, grid_for(D, (long long)n_qs * MFSC_LANES, 128, 16), 128, 0, D.stream, s_s1, s_s2, s_len, s_rec, seg, n_qs, P, W, O);
+    MFSC_LAUNCH(k_cluster, grid_for(D, ((long long)n_qs + 7) / 8 * MFSC_LANES, 128, 16), 128, 0, D.stream, s_s1, s_s2, s_len, s_rec, seg, n_qs, P, W, O, d_counter + 5);
     D.launches++;
     stamp(D, ts[3]);
 

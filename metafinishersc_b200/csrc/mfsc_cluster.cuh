@@ -38,9 +38,17 @@ MFSC_DEV int uf_find(int* uf, int a) {
 MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
 
 MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
-                      int n_qs, DevParams P, ClusterScratch W, ClusterOut O) {
+                      int n_qs, DevParams P, ClusterScratch W, ClusterOut O, unsigned* ticket) {
   const int lane = lane_id();
-  for (long long qs = warp_global(); qs < n_qs; qs += warps_total()) {
+  // strands are handed out by a ticket counter, 8 at a time: the forward strands carry nearly all matches of a
+  // reads-vs-contigs batch, so a static round-robin leaves every other warp without work
+  for (;;) {
+    unsigned q0 = 0;
+    if (lane == 0) q0 = atomic_add_u32(ticket, 8u);
+    q0 = (unsigned)wbcast_i32((int)q0, 0);
+    if (q0 >= (unsigned)n_qs) break;
+    const unsigned q1 = q0 + 8u < (unsigned)n_qs ? q0 + 8u : (unsigned)n_qs;
+  for (unsigned qs = q0; qs < q1; qs++) {
     const int b = seg[qs], e = seg[qs + 1];
     const int n = e - b;
     if (n <= 0) {
@@ -323,5 +331,6 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
       c0 = c1;
     }
     if (lane == 0) { O.n_pc[qs] = n_pc; O.n_cm[qs] = n_cm; }
+  }
   }
 }

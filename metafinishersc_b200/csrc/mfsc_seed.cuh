@@ -40,57 +40,307 @@ MFSC_DEV unsigned mem_slot(unsigned* ctr) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------------
+// Stage 2 kernel.  A warp owns one tile of a query strand (SEED_TILE_WORDS packed words = 2048 bases):
+//   a. the tile's packed text and invalid mask are staged in shared memory with 128-bit / 64-bit coalesced loads
+//      (one load per lane), and every probe window is then cut out of shared memory;
+//   b. all lanes probe together, SEED_U probes per lane and round: k-mer -> one bit of the bucket occupancy bitmap
+//      (4^k / 8 bytes, resident in L2) -> only occupied buckets touch the bucket heads (the one table far larger
+//      than L2), SEED_U independent loads in flight per lane;
+//   c. the probes that found candidates are compacted into a shared-memory list (ballot + popc) and dealt to the
+//      lanes one probe each, so the lanes verifying candidates are the ones that have any; buckets with more than
+//      SEED_HEAVY positions (repeats) are walked by the whole warp, 32 positions at a time;
+//   d. a match that is still running after SEED_LONG bases is finished by the whole warp, 32 words (1024 bases)
+//      per step -- whole-contig matches of a self-alignment (reference call shapes #2/#3/#5/#7 of SURVEY appendix A).
+// Matches are appended with a warp-aggregated atomic; their order is fixed by the sort that follows.
+// ------------------------------------------------------------------------------------------
+#define SEED_TILE_WORDS 64
+#define SEED_TILE_BASES (SEED_TILE_WORDS * 32)
+#define SEED_STAGE (SEED_TILE_WORDS + 2)      // words staged: a window may start in the tile's last word
+#define SEED_U 4
+#define SEED_HEAVY 8
+#define SEED_LONG 256
+#define SEED_WARPS 4                          // warps per block
+
+struct SeedTiles {
+  const unsigned* tile_off;   // [n_qs + 1] first tile of every query strand (a strand of len bases has ceil(len / 2048) tiles)
+  unsigned n_tiles;
+  unsigned* ticket;
+};
+
+struct SeedShared {
+  unsigned long long txt[SEED_STAGE];
+  unsigned inv[SEED_STAGE];
+  unsigned l_b0[MFSC_LANES * SEED_U]; unsigned l_b1[MFSC_LANES * SEED_U]; int l_p[MFSC_LANES * SEED_U];     // probes with candidates
+  unsigned g_r[MFSC_LANES * 2]; int g_p[MFSC_LANES * 2]; int g_left[MFSC_LANES * 2]; int g_right[MFSC_LANES * 2];   // long matches
+};
+
+MFSC_DEV unsigned long long sm_win64(const unsigned long long* txt, int pos) {
+  const int w = pos >> 5; const unsigned sh = (unsigned)(pos & 31) * 2u;
+  const unsigned long long lo = txt[w];
+  if (sh == 0) return lo;
+  return (lo >> sh) | (txt[w + 1] << (64u - sh));
+}
+MFSC_DEV unsigned sm_win32(const unsigned* inv, int pos) {
+  const int w = pos >> 5; const unsigned sh = (unsigned)(pos & 31);
+  const unsigned lo = inv[w];
+  if (sh == 0) return lo;
+  return (lo >> sh) | (inv[w + 1] << (32u - sh));
+}
+
+struct SeedCtx {
+  SeqStore R, Q; const unsigned* r_ostart; const unsigned* H; const unsigned* pos; DevParams P; MemOut out;
+  unsigned qstart; int qlen, qs;
+};
+
+// one candidate (reference position r of a k-mer equal to the probe at p).  Returns 1 when the match has to be
+// finished by the warp (left in *left_o, bases matched so far to the right in *right_o), 0 otherwise.
+MFSC_DEV int seed_candidate(const SeedCtx& C, unsigned r, int p, int* left_o, int* right_o) {
+  const int k = C.P.k, s = C.P.stride;
+  const unsigned qp = C.qstart + (unsigned)p;
+  const int maxl = p < s ? p : s;
+  const int left = match_left(C.R, r, C.Q, qp, maxl);
+  if (left >= s) return 0;                        // an earlier probe owns this match
+  const int lim = C.qlen - p - k;
+  const int first = lim < SEED_LONG ? lim : SEED_LONG;
+  const int right = match_right(C.R, r + k, C.Q, qp + k, first);
+  *left_o = left; *right_o = right;
+  return (right >= first && first < lim) ? 1 : 2;
+}
+
+MFSC_DEV void seed_emit(const SeedCtx& C, unsigned r, int p, int left, int right) {
+  const int k = C.P.k;
+  const int total = left + k + right;
+  if (total < C.P.minmatch) return;
+  const unsigned s1p = r - (unsigned)left;
+  const int s2 = p - left;
+  if (!C.P.maxmatch) {
+    // -mumreference: the matched string must occur exactly once in the reference
+    const unsigned long long kmask = (1ull << (2 * k)) - 1ull;
+    const unsigned long long km0 = win64(C.Q.txt, C.qstart + (unsigned)s2) & kmask;
+    bool unique = true;
+    for (unsigned g = C.H[km0]; g < C.H[km0 + 1] && unique; g++) {
+      const unsigned r2 = C.pos[g];
+      if (r2 == s1p) continue;
+      if (match_right(C.R, r2 + k, C.Q, C.qstart + (unsigned)s2 + k, total - k) >= total - k) unique = false;
+    }
+    if (!unique) return;
+  }
+  const unsigned slot = mem_slot(&C.out.counter[0]);
+  if (slot < C.out.capacity) {
+    const int rec = seq_of(C.R.start, C.R.n_seq, s1p);
+    C.out.qs[slot] = C.qs;
+    C.out.s1[slot] = s1p - C.R.start[rec] + C.r_ostart[rec];
+    C.out.s2[slot] = s2;
+    C.out.len[slot] = total;
+    C.out.rec[slot] = rec;
+  }
+}
+
+// the whole warp finishes one long match: words of 32 bases, one per lane and step
+MFSC_DEV int seed_finish_long(const SeedCtx& C, unsigned r, int p, int right, int lane) {
+  const int k = C.P.k;
+  const unsigned rp = r + (unsigned)k, qp = C.qstart + (unsigned)(p + k);
+  const int lim = C.qlen - p - k;
+  int n = right;
+  for (;;) {
+    const int off = n + 32 * lane;
+    int m = 32;
+    if (off < lim) {
+      const unsigned long long x = win64(C.R.txt, rp + off) ^ win64(C.Q.txt, qp + off);
+      const unsigned long long mm = (x | (x >> 1)) & MFSC_EVEN;
+      const unsigned ia = win32(C.R.inv, rp + off) | win32(C.Q.inv, qp + off);
+      const int t = mm ? ((dev_ffs64(mm) - 1) >> 1) : 32;
+      const int u = ia ? (dev_ffs32(ia) - 1) : 32;
+      m = t < u ? t : u;
+      if (off + m > lim) m = lim - off;
+    } else m = 0;
+    const unsigned stop = wballot(m < 32);
+    if (stop) {
+      const int first = dev_ffs32(stop) - 1;
+      return n + 32 * first + wbcast_i32(m, first);
+    }
+    n += 32 * MFSC_LANES;
+  }
+}
+
 // R: reference store; r_ostart[rec] = position of record rec's first base in the separator-joined
-// coordinate system the clustering stage works in (off[rec] + rec).
-MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, const unsigned* pos, SeqStore Q,
-                    const ProbeChunk* chunks, int n_chunks, DevParams P, MemOut out) {
-  const int k = P.k, s = P.stride, L = P.minmatch;
+// coordinate system the clustering stage works in (off[rec] + rec).  occ: one bit per bucket, set when it is not empty.
+MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, const unsigned* pos, const unsigned* occ, SeqStore Q,
+                    SeedTiles T, DevParams P, MemOut out) {
+#ifdef MFSC_EMU
+  static thread_local SeedShared sm_all[1];
+  SeedShared& S = sm_all[0];
+#else
+  __shared__ SeedShared sm_all[SEED_WARPS];
+  SeedShared& S = sm_all[warp_in_block()];
+#endif
+  const int lane = lane_id();
+  const int k = P.k, s = P.stride;
   const unsigned long long kmask = (1ull << (2 * k)) - 1ull;
   const unsigned vmask = (1u << k) - 1u;
-  for (int c = (int)blockIdx.x; c < n_chunks; c += (int)gridDim.x) {
-    const ProbeChunk ch = chunks[c];
-    const unsigned qstart = Q.start[ch.qs];
-    const int qlen = Q.len[ch.qs];
-    for (int i = ch.pb + (int)threadIdx.x; i < ch.pe; i += (int)blockDim.x) {
-      const int p = i * s;
-      const unsigned qp = qstart + (unsigned)p;
-      if (win32(Q.inv, qp) & vmask) continue;
-      const unsigned long long km = win64(Q.txt, qp) & kmask;
-      // the bucket heads (1/4 GB and up) are touched once per probe at random: stream them through L2 so that the
-      // position table and the packed reference text, which every candidate re-reads, stay resident
-      const unsigned b0 = ld_stream(&H[km]), b1 = ld_stream(&H[km + 1]);
-      for (unsigned h = b0; h < b1; h++) {
-        const unsigned r = pos[h];
-        const int maxl = p < s ? p : s;
-        const int left = match_left(R, r, Q, qp, maxl);
-        if (left >= s) continue;  // an earlier probe owns this match
-        const int right = match_right(R, r + k, Q, qp + k, qlen - p - k);
-        const int total = left + k + right;
-        if (total < L) continue;
-        const unsigned s1p = r - (unsigned)left;
-        const int s2 = p - left;
-        if (!P.maxmatch) {
-          // -mumreference: the matched string must occur exactly once in the reference
-          const unsigned long long km0 = win64(Q.txt, qstart + (unsigned)s2) & kmask;
-          bool unique = true;
-          for (unsigned g = H[km0]; g < H[km0 + 1] && unique; g++) {
-            const unsigned r2 = pos[g];
-            if (r2 == s1p) continue;
-            if (match_right(R, r2 + k, Q, qstart + (unsigned)s2 + k, total - k) >= total - k) unique = false;
-          }
-          if (!unique) continue;
-        }
-        const unsigned slot = mem_slot(&out.counter[0]);
-        if (slot < out.capacity) {
-          const int rec = seq_of(R.start, R.n_seq, s1p);
-          out.qs[slot] = ch.qs;
-          out.s1[slot] = s1p - R.start[rec] + r_ostart[rec];
-          out.s2[slot] = s2;
-          out.len[slot] = total;
-          out.rec[slot] = rec;
+  const unsigned lt_mask = MFSC_LANES == 32 ? ((1u << lane) - 1u) : 0u;
+  SeedCtx C; C.R = R; C.Q = Q; C.r_ostart = r_ostart; C.H = H; C.pos = pos; C.P = P; C.out = out;
+  const unsigned TICKET = 4;                     // consecutive tiles per ticket: the strand is looked up once per ticket
+  for (;;) {
+    unsigned t0 = 0;
+    if (lane == 0) t0 = atomic_add_u32(T.ticket, TICKET);
+    t0 = (unsigned)wbcast_i32((int)t0, 0);
+    if (t0 >= T.n_tiles) break;
+    const unsigned t1 = t0 + TICKET < T.n_tiles ? t0 + TICKET : T.n_tiles;
+    int qs = seq_of(T.tile_off, Q.n_seq, t0);
+    for (unsigned t = t0; t < t1; t++) {
+      while (T.tile_off[qs + 1] <= t) qs++;
+      const int tile = (int)(t - T.tile_off[qs]);
+      const unsigned qstart = Q.start[qs];
+      const int qlen = Q.len[qs];
+      C.qstart = qstart; C.qlen = qlen; C.qs = qs;
+      const int base0 = tile * SEED_TILE_BASES;              // first base of the tile on the strand
+      const int np = qlen >= k ? (qlen - k) / s + 1 : 0;     // probes of the strand: positions 0, s, 2s, ...
+      const int pb = (base0 + s - 1) / s;
+      int pe = (base0 + SEED_TILE_BASES + s - 1) / s;
+      if (pe > np) pe = np;
+      if (pb >= pe) continue;
+      // a. stage the tile: lane l takes words 2l, 2l+1 (one 128-bit load of text, one 64-bit load of the mask);
+      //    two more words for the windows that start in the last word.  Words past the strand's end are padding
+      //    inside the buffer (layout in mfsc_seq.cuh) or clamped to its last word.
+      wsync();
+      {
+        const unsigned w0 = (qstart >> 5) + (unsigned)tile * SEED_TILE_WORDS;
+        const unsigned wmax = Q.n_words - 1u;
+        for (int x = 2 * lane; x < SEED_STAGE; x += 2 * MFSC_LANES) {
+          const unsigned wa = w0 + (unsigned)x < wmax ? w0 + (unsigned)x : wmax, wb = w0 + (unsigned)x + 1u < wmax ? w0 + (unsigned)x + 1u : wmax;
+#if !defined(MFSC_EMU)
+          if (wb == wa + 1u && (wa & 1u) == 0u) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(Q.txt + wa);
+            const uint2 iv = *reinterpret_cast<const uint2*>(Q.inv + wa);
+            S.txt[x] = v.x; S.txt[x + 1] = v.y; S.inv[x] = iv.x; S.inv[x + 1] = iv.y;
+          } else
+#endif
+          { S.txt[x] = Q.txt[wa]; S.txt[x + 1] = Q.txt[wb]; S.inv[x] = Q.inv[wa]; S.inv[x + 1] = Q.inv[wb]; }
         }
       }
+      wsync();
+      for (int i0 = pb; i0 < pe; i0 += MFSC_LANES * SEED_U) {
+        // b. SEED_U probes per lane: k-mer, occupancy bit, bucket bounds of the occupied ones
+        unsigned long long km[SEED_U]; bool live[SEED_U]; unsigned b0[SEED_U], b1[SEED_U];
+#pragma unroll
+        for (int u = 0; u < SEED_U; u++) {
+          const int i = i0 + u * MFSC_LANES + lane;
+          const int lp = i * s - base0;                       // probe position inside the staged tile
+          live[u] = i < pe;
+          km[u] = 0;
+          if (live[u]) {
+            live[u] = (sm_win32(S.inv, lp) & vmask) == 0u;
+            km[u] = sm_win64(S.txt, lp) & kmask;
+          }
+        }
+        unsigned ow[SEED_U];
+#pragma unroll
+        for (int u = 0; u < SEED_U; u++) ow[u] = live[u] ? ldg(&occ[km[u] >> 5]) : 0u;
+#pragma unroll
+        for (int u = 0; u < SEED_U; u++) {
+          live[u] = ((ow[u] >> (unsigned)(km[u] & 31ull)) & 1u) != 0u;
+          b0[u] = 0; b1[u] = 0;
+          // the bucket heads (1/4 GB and up) are touched once per occupied probe at random: stream them through L2 so
+          // that the bitmap, the position table and the packed reference text, which are reused, stay resident
+          if (live[u]) { b0[u] = ld_stream(&H[km[u]]); b1[u] = ld_stream(&H[km[u] + 1]); }
+        }
+        // c. probes with candidates -> shared list (light buckets first, heavy ones from the top)
+        int n_light = 0, n_heavy = 0;
+#pragma unroll
+        for (int u = 0; u < SEED_U; u++) {
+          const unsigned cnt = b1[u] - b0[u];
+          const bool lt = cnt > 0u && cnt <= SEED_HEAVY, hv = cnt > SEED_HEAVY;
+          const unsigned ml = wballot(lt), mh = wballot(hv);
+          const int p = (i0 + u * MFSC_LANES + lane) * s;
+          if (lt) { const int w = n_light + dev_popc32(ml & lt_mask); S.l_b0[w] = b0[u]; S.l_b1[w] = b1[u]; S.l_p[w] = p; }
+          if (hv) { const int w = MFSC_LANES * SEED_U - 1 - n_heavy - dev_popc32(mh & lt_mask); S.l_b0[w] = b0[u]; S.l_b1[w] = b1[u]; S.l_p[w] = p; }
+          n_light += dev_popc32(ml); n_heavy += dev_popc32(mh);
+        }
+        if (n_light + n_heavy == 0) continue;
+        wsync();
+        int n_long = 0;
+        // light buckets: one probe per lane
+        for (int x0 = 0; x0 < n_light; x0 += MFSC_LANES) {
+          const int x = x0 + lane;
+          unsigned h = 0, he = 0; int p = 0;
+          if (x < n_light) { h = S.l_b0[x]; he = S.l_b1[x]; p = S.l_p[x]; }
+          for (int step = 0; step < SEED_HEAVY; step++) {
+            int kind = 0, left = 0, right = 0; unsigned r = 0;
+            if (h < he) { r = pos[h]; kind = seed_candidate(C, r, p, &left, &right); h++; }
+            if (kind == 2) seed_emit(C, r, p, left, right);
+            const unsigned ml = wballot(kind == 1);
+            if (ml) {
+              if (kind == 1) { const int w = n_long + dev_popc32(ml & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; S.g_right[w] = right; }
+              n_long += dev_popc32(ml);
+              wsync();
+              if (n_long > MFSC_LANES) {            // keep room for another 32
+                for (int g = 0; g < n_long; g++) {
+                  const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
+                  const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
+                  if (lane == 0) seed_emit(C, gr, gp, gl, tot);
+                }
+                n_long = 0;
+                wsync();
+              }
+            }
+            if (wballot(h < he) == 0u) break;
+          }
+        }
+        // heavy buckets: the warp walks one bucket at a time
+        for (int y = 0; y < n_heavy; y++) {
+          const int e = MFSC_LANES * SEED_U - 1 - y;
+          const unsigned hb = S.l_b0[e], he = S.l_b1[e]; const int p = S.l_p[e];
+          for (unsigned h0 = hb; h0 < he; h0 += MFSC_LANES) {
+            const unsigned h = h0 + (unsigned)lane;
+            int kind = 0, left = 0, right = 0; unsigned r = 0;
+            if (h < he) { r = pos[h]; kind = seed_candidate(C, r, p, &left, &right); }
+            if (kind == 2) seed_emit(C, r, p, left, right);
+            const unsigned ml = wballot(kind == 1);
+            if (ml) {
+              if (kind == 1) { const int w = n_long + dev_popc32(ml & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; S.g_right[w] = right; }
+              n_long += dev_popc32(ml);
+              wsync();
+              if (n_long > MFSC_LANES) {
+                for (int g = 0; g < n_long; g++) {
+                  const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
+                  const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
+                  if (lane == 0) seed_emit(C, gr, gp, gl, tot);
+                }
+                n_long = 0;
+                wsync();
+              }
+            }
+          }
+        }
+        // d. long matches left over
+        wsync();
+        for (int g = 0; g < n_long; g++) {
+          const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
+          const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
+          if (lane == 0) seed_emit(C, gr, gp, gl, tot);
+        }
+        wsync();
+      }
     }
+  }
+}
+
+// occupancy bitmap of the bucket table: bit b of word w is set when bucket 32 w + b holds at least one position
+MFSC_KERNEL k_index_occ(const unsigned* H, long long n_buckets, unsigned* occ) {
+  const long long n_words = (n_buckets + 31) / 32;
+  for (long long w = thread_global(); w < n_words; w += threads_total()) {
+    unsigned bits = 0;
+    unsigned prev = H[w * 32];
+    for (int b = 0; b < 32; b++) {
+      const long long x = w * 32 + b;
+      if (x >= n_buckets) break;
+      const unsigned nx = H[x + 1];
+      if (nx > prev) bits |= 1u << b;
+      prev = nx;
+    }
+    occ[w] = bits;
   }
 }
 

@@ -40,15 +40,15 @@ class Index:
     def info(self):
         a = np.zeros(8, dtype=np.int64)
         check(self.L, self.L.mfsc_index_info(self.h, ptr(a)))
-        return dict(k=int(a[0]), text_words=int(a[2]), buckets=int(a[3]), positions=int(a[4]), hbm_bytes=int(a[5]),
+        return dict(k=int(a[0]), device=int(a[1]), text_words=int(a[2]), buckets=int(a[3]), positions=int(a[4]), hbm_bytes=int(a[5]),
                     records=int(a[6]), bases=int(a[7]))
 
     def buffers(self):
-        """[(device pointer, bytes)] x 4: packed text, invalid mask, bucket heads, positions."""
-        p = (ctypes.c_void_p * 4)()
-        b = np.zeros(4, dtype=np.int64)
+        """[(device pointer, bytes)] x 5: packed text, invalid mask, bucket heads, positions, occupancy bitmap."""
+        p = (ctypes.c_void_p * 5)()
+        b = np.zeros(5, dtype=np.int64)
         check(self.L, self.L.mfsc_index_buffers(self.h, p, ptr(b)))
-        return [(int(p[i] or 0), int(b[i])) for i in range(4)]
+        return [(int(p[i] or 0), int(b[i])) for i in range(5)]
 
     def build_ms(self):
         v = ctypes.c_double()
@@ -131,6 +131,10 @@ class Engine:
 
     def set_device(self, d):
         check(self.L, self.L.mfsc_set_device(d))
+
+    def thread_release(self):
+        """Destroys the calling thread's stream (worker threads call it before they end)."""
+        self.L.mfsc_thread_release()
 
     # -- stage 1 ---------------------------------------------------------------------------
     def index(self, contigs, params=None, build_tables=True, n_positions=0):

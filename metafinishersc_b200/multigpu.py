@@ -1,44 +1,84 @@
-"""One process per GPU: the contig index is built on rank 0 and replicated with one NCCL broadcast
-per buffer over NVLink (torch.distributed); reads shard by batch, so alignment itself needs no
-collective (the reference's analogue is the 20-part fan-out of
-alignerRobot.useMummerAlignBatch, alignerRobot.py:114-166).
+"""Several GPUs of one box: the contig index is built ONCE and replicated with one NCCL broadcast per buffer over
+NVLink (`mfsc_index_broadcast` in the C ABI); reads shard by batch, so alignment itself needs no collective
+(the reference's analogue is the 20-part fan-out of alignerRobot.useMummerAlignBatch,
+alignerRobot.py:114-166, where every job rebuilds the suffix tree of the whole reference).
+
+Two launch shapes:
+  * one process, one host thread per GPU (`LocalClique`): what alignerRobot._batch_on_gpus uses;
+  * one process per GPU under torchrun (`RankComm`): the 128-byte NCCL id travels through torch.distributed
+    (plumbing), the broadcast itself is the library's.
 """
-import time
+import ctypes
 
 import numpy as np
 
-
-class _DevBuf:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+from . import _lib
+from .engine import Index
 
 
-def replicated_index(E, contigs, params, rank, world):
-    """Returns (index, broadcast_ms).  world == 1: plain build."""
+class LocalClique:
+    """NCCL communicators over `devices` of this process (ncclCommInitAll)."""
+
+    def __init__(self, E, devices):
+        self.L, self.devices = E.L, list(devices)
+        dv = np.ascontiguousarray(self.devices, dtype=np.int32)
+        h = ctypes.c_void_p()
+        _lib.check(self.L, self.L.mfsc_comm_init_local(_lib.ptr(dv), len(dv), ctypes.byref(h)))
+        self.h = h
+
+    def broadcast(self, index, root=0):
+        """index: the built Index living on devices[root].  Returns ([Index per device], ms); entry `root` is `index`."""
+        n = len(self.devices)
+        arr = (ctypes.c_void_p * n)()
+        arr[root] = index.h
+        ms = ctypes.c_double()
+        _lib.check(self.L, self.L.mfsc_index_broadcast(self.h, root, arr, ctypes.byref(ms)))
+        out = [index if i == root else Index(self.L, ctypes.c_void_p(arr[i]), index.n_rec) for i in range(n)]
+        return out, ms.value
+
+    def free(self):
+        if self.h:
+            self.L.mfsc_comm_free(self.h)
+            self.h = None
+
+
+class RankComm:
+    """One rank of a one-process-per-GPU job.  `exchange(buf, src)` must broadcast a uint8 numpy array of 128 bytes from
+    rank `src` to all ranks in place (torch.distributed in bench.py; anything else works as well)."""
+
+    def __init__(self, E, rank, world, exchange):
+        self.L, self.rank, self.world = E.L, rank, world
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self.L, self.L.mfsc_comm_unique_id(_lib.ptr(uid)))
+        exchange(uid, 0)
+        h = ctypes.c_void_p()
+        _lib.check(self.L, self.L.mfsc_comm_init_rank(_lib.ptr(uid), rank, world, ctypes.byref(h)))
+        self.h = h
+
+    def broadcast(self, index, n_rec, root=0):
+        """index: the built Index on the root rank, None elsewhere.  Returns (Index, ms)."""
+        arr = (ctypes.c_void_p * 1)()
+        arr[0] = index.h if index is not None else None
+        ms = ctypes.c_double()
+        _lib.check(self.L, self.L.mfsc_index_broadcast(self.h, root, arr, ctypes.byref(ms)))
+        if index is None:
+            index = Index(self.L, ctypes.c_void_p(arr[0]), n_rec)
+        return index, ms.value
+
+    def free(self):
+        if self.h:
+            self.L.mfsc_comm_free(self.h)
+            self.h = None
+
+
+def replicated_index(E, contigs, params, rank, world, comm=None):
+    """Rank 0 builds, every rank receives (RankComm).  Returns (index, broadcast_ms).  world == 1: plain build."""
     if world == 1:
         return E.index(contigs, params), 0.0
-    import torch
-    import torch.distributed as dist
-    meta = torch.zeros(2, dtype=torch.int64, device="cuda")
-    ix = None
-    if rank == 0:
-        ix = E.index(contigs, params)
-        info = ix.info()
-        meta[0], meta[1] = info["k"], info["positions"]
-    dist.broadcast(meta, src=0)
-    if rank != 0:
-        params.kmer = int(meta[0].item())
-        ix = E.index(contigs, params, build_tables=False, n_positions=int(meta[1].item()))
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for ptr, nbytes in ix.buffers():
-        t = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
-        dist.broadcast(t, src=0)
-    torch.cuda.synchronize()
-    return ix, (time.perf_counter() - t0) * 1e3
+    ix = E.index(contigs, params) if rank == 0 else None
+    n_rec = len(contigs[1]) - 1 if isinstance(contigs, tuple) else len(contigs)
+    return comm.broadcast(ix, n_rec, root=0)
 
 
 def shard_reads(n_reads, rank, world):
