@@ -278,30 +278,37 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
         for outputName, referenceName, queryName, specialName in workerList:
             useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
         return
+    # globalLarge (alignerRobot.py:168-236): reference and query are each split into 10 parts (written to the CWD, where
+    # fasta-splitter.pl puts them), every (reference part i, query part j) tile is its own nucmer job
+    # `<folder><out>IIJJ.delta`, and the coords file is `head -5` of tile (01, 01) followed by `tail -n+6` of every tile,
+    # i outer, j inner.  The tiles are run for real: a cluster that spans two reference records (mgaps chains over the
+    # concatenated reference) exists only when both records are in the same part, so re-ordering the rows of one whole
+    # alignment would not give the same table.
     n_parts = 10
+    params = _params(refinedVersion)
     for outputName, referenceName, queryName, specialName in workerList:
-        rs = nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion)
+        qry_full = queryName if specialForRaw else folderName + queryName
+        for path in (folderName + referenceName, qry_full):
+            if os.path.exists(path):
+                fasta.split_fasta(path, n_parts, out_dir=os.getcwd())
         out = folderName + (specialName if specialForRaw else outputName + "Out")
-        if rs is None:
-            open(out, "w").close()
-            continue
-        # tiles are written reference part by reference part, query part by query part (alignerRobot.py:226-236)
-        rn, rseq = fasta.read_fasta(rs.ref_path)
-        qn, qseq = fasta.read_fasta(rs.qry_path)
-        rpart = np.zeros(len(rn), dtype=np.int64)
-        for p, (b, e) in enumerate(fasta.part_boundaries(rn, rseq, n_parts)):
-            rpart[b:e] = p
-        qpart = np.zeros(len(qn), dtype=np.int64)
-        for p, (b, e) in enumerate(fasta.part_boundaries(qn, qseq, n_parts)):
-            qpart[b:e] = p
-        r = rs.rows
-        base = rs.order()
-        key = np.lexsort((np.arange(len(base)), qpart[r.qry_id[base]], rpart[r.ref_id[base]]))
-        sel = base[key]
-        sub = _engine_mod.Rows()
-        for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
-            setattr(sub, f, np.ascontiguousarray(getattr(r, f)[sel]))
-        get_engine().write_coords(out, sub, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=False)
+        lines, header = [], None
+        for i in range(1, n_parts + 1):
+            for j in range(1, n_parts + 1):
+                tmpRef = referenceName[0:-6] + ".part-" + zeropadding(i) + ".fasta"
+                tmpQry = queryName[0:-6] + ("-" if specialForRaw else ".part-") + zeropadding(j) + ".fasta"
+                prefix = folderName + outputName + zeropadding(i) + zeropadding(j)
+                rs = _run_nucmer(prefix, tmpRef, tmpQry, params)
+                tile_out = prefix + ".coords.tmp"
+                _write_coords(rs, tile_out)
+                with open(tile_out) as f:
+                    tl = f.readlines()
+                os.remove(tile_out)
+                if i == 1 and j == 1:
+                    header = tl[:5]
+                lines += tl[5:]
+        with open(out, "w") as f:
+            f.writelines((header or []) + lines)
 
 
 def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus):

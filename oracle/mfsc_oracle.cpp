@@ -296,7 +296,7 @@ struct Aln {
   std::string ops;     // one char per alignment column: 'M' pair, 'I' A-only (delta > 0), 'D' B-only (delta < 0)
 };
 
-struct Stats { i64 cells; i64 max_band; i64 dp_calls; };
+struct Stats { i64 cells; i64 max_band; i64 dp_calls; i64 cap_hits; };   // cap_hits: diagonals on which band_cap trimmed the band
 
 // base accessors: A = one reference record (1-based local), B = query strand (1-based)
 struct View {
@@ -380,6 +380,7 @@ EngOut engine(const View& Av, i64 a0, const View& Bv, i64 b0, int dirn, i64 N, i
     i64 lo = nlo, hi = nhi;
     while (lo <= nhi && high - mx[lo - nlo] > max_diff) lo++;
     while (hi >= nlo && high - mx[hi - nlo] > max_diff) hi--;
+    if (lo <= hi && hi - lo + 2 > P.band_cap) st.cap_hits++;
     while (lo <= hi && hi - lo + 2 > P.band_cap) { if (mx[lo - nlo] < mx[hi - nlo]) lo++; else hi--; }
     nlo = std::max<i64>(lo, d + 1 - N);
     nhi = std::min<i64>(hi + 1, std::min<i64>(d + 1, M));
@@ -585,10 +586,8 @@ void finish_alignment(const Aln& a, const View& A, const View& B, int ref, int q
   R.rows.push_back(r);
 }
 
-void run(const SeqSet& Rf, const SeqSet& Q, const Params& P, int stage_limit, Result& R) {
-  int k = std::min(P.minmatch, 12);
-  KIndex ix; build_index(Rf, k, ix);
-  R.st.cells = 0; R.st.max_band = 0; R.st.dp_calls = 0;
+void run(const SeqSet& Rf, const KIndex& ix, const SeqSet& Q, const Params& P, int stage_limit, Result& R) {
+  R.st.cells = 0; R.st.max_band = 0; R.st.dp_calls = 0; R.st.cap_hits = 0;
   std::vector<uint8_t> fw, rc;
   for (int q = 0; q < Q.n(); q++) {
     i64 L = Q.len[q];
@@ -662,9 +661,48 @@ void* orc_run(const char* ref, const int64_t* ref_off, int n_ref, const char* qr
   P.diagdiff = p->diagdiff; P.diagfactor = p->diagfactor; P.maxmatch = p->maxmatch; P.simplify = p->simplify;
   P.band_cap = p->band_cap;
   SeqSet Rf, Q; load(Rf, ref, ref_off, n_ref); load(Q, qry, qry_off, n_qry);
+  KIndex ix; build_index(Rf, std::min(P.minmatch, 12), ix);
   Result* R = new Result();
-  run(Rf, Q, P, stage_limit, *R);
+  run(Rf, ix, Q, P, stage_limit, *R);
   return R;
+}
+
+// The reference set loaded and indexed once, then shared (read-only) by any number of threads calling orc_run_ix:
+// what the timed CPU arm of bench.py uses, so that no thread rebuilds the k-mer index per call.
+struct RefHandle { SeqSet Rf; KIndex ix; };
+void* orc_ref_build(const char* ref, const int64_t* ref_off, int n_ref, int minmatch) {
+  RefHandle* h = new RefHandle();
+  load(h->Rf, ref, ref_off, n_ref);
+  build_index(h->Rf, std::min(minmatch, 12), h->ix);
+  return h;
+}
+void orc_ref_free(void* h) { delete (RefHandle*)h; }
+void* orc_run_ix(void* ref_handle, const char* qry, const int64_t* qry_off, int n_qry, const orc_params* p, int stage_limit) {
+  RefHandle* h = (RefHandle*)ref_handle;
+  Params P; P.minmatch = p->minmatch; P.mincluster = p->mincluster; P.maxgap = p->maxgap; P.breaklen = p->breaklen;
+  P.diagdiff = p->diagdiff; P.diagfactor = p->diagfactor; P.maxmatch = p->maxmatch; P.simplify = p->simplify;
+  P.band_cap = p->band_cap;
+  if (h->ix.k > P.minmatch) return 0;
+  SeqSet Q; load(Q, qry, qry_off, n_qry);
+  Result* R = new Result();
+  run(h->Rf, h->ix, Q, P, stage_limit, *R);
+  return R;
+}
+
+// One run of the DP engine on two plain sequences (test hook for oracle/bruteforce.py): a[0..n), b[0..m) as characters,
+// forward direction from (1, 1).  out: reached, fi, fj; ops (at most n + m + 1 chars, NUL-terminated): 'M' pair, 'I' a-only, 'D' b-only.
+void orc_dp(const char* a, int n, const char* b, int m, int breaklen, int band_cap, int forced, int optimal, int64_t* out, char* ops_out) {
+  std::vector<uint8_t> ca(n), cb(m);
+  for (int i = 0; i < n; i++) ca[i] = (uint8_t)code_of(a[i]);
+  for (int i = 0; i < m; i++) cb[i] = (uint8_t)code_of(b[i]);
+  Params P; P.minmatch = 20; P.mincluster = 65; P.maxgap = 90; P.breaklen = breaklen; P.diagdiff = 5; P.diagfactor = 0.12;
+  P.maxmatch = 1; P.simplify = 1; P.band_cap = band_cap;
+  View A, B; A.p = ca.data(); A.n = n; B.p = cb.data(); B.n = m;
+  Stats st; st.cells = 0; st.max_band = 0; st.dp_calls = 0; st.cap_hits = 0;
+  std::string ops;
+  EngOut o = engine(A, 1, B, 1, +1, n, m, false, forced != 0, optimal != 0, P, &ops, st);
+  out[0] = o.reached ? 1 : 0; out[1] = o.fi; out[2] = o.fj; out[3] = st.cells; out[4] = st.max_band;
+  memcpy(ops_out, ops.c_str(), ops.size() + 1);
 }
 
 void orc_free(void* h) { delete (Result*)h; }
@@ -708,7 +746,7 @@ void orc_get_rows(void* h, int64_t* out, int64_t* deltas) {
   if (deltas) for (size_t i = 0; i < R->deltas.size(); i++) deltas[i] = R->deltas[i];
 }
 void orc_get_stats(void* h, int64_t* out) {
-  Result* R = (Result*)h; out[0] = R->st.cells; out[1] = R->st.max_band; out[2] = R->st.dp_calls;
+  Result* R = (Result*)h; out[0] = R->st.cells; out[1] = R->st.max_band; out[2] = R->st.dp_calls; out[3] = R->st.cap_hits;
 }
 
 // Coverage profile, restating srcRefactor/misassemblyFixerLib/merger.py:126-140 (assignCoverage):

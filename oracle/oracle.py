@@ -48,6 +48,13 @@ def lib():
         L.orc_get_clusters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_get_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_ref_build.restype = ctypes.c_void_p
+        L.orc_ref_build.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.orc_ref_free.argtypes = [ctypes.c_void_p]
+        L.orc_run_ix.restype = ctypes.c_void_p
+        L.orc_run_ix.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_Params), ctypes.c_int]
+        L.orc_dp.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                             ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]
         L.orc_coverage.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -66,6 +73,38 @@ def _concat(seqs):
     return b"".join(bs), off
 
 
+class Ref:
+    """Reference records loaded and indexed once; `align(ref, reads)` calls may then share it from many threads
+    (ctypes releases the GIL), which is how bench.py's CPU arm uses all host cores without rebuilding the index."""
+
+    def __init__(self, ref_seqs, minmatch=20):
+        rb, roff = _concat(ref_seqs)
+        self.n = len(ref_seqs)
+        self.h = lib().orc_ref_build(rb, roff.ctypes.data, self.n, minmatch)
+
+    def free(self):
+        if self.h:
+            lib().orc_ref_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def dp(a, b, breaklen=200, band_cap=1 << 20, forced=False, optimal=False):
+    """One run of the oracle's DP engine on two sequences (forward from their first bases).  Returns
+    dict(reached, fi, fj, cells, max_band, ops) -- ops: 'M' pair column, 'I' a-only, 'D' b-only."""
+    a = a.encode() if isinstance(a, str) else bytes(a)
+    b = b.encode() if isinstance(b, str) else bytes(b)
+    out = np.zeros(8, dtype=np.int64)
+    buf = ctypes.create_string_buffer(len(a) + len(b) + 8)
+    lib().orc_dp(a, len(a), b, len(b), breaklen, band_cap, int(forced), int(optimal), out.ctypes.data, buf)
+    return dict(reached=bool(out[0]), fi=int(out[1]), fj=int(out[2]), cells=int(out[3]), max_band=int(out[4]), ops=buf.value.decode())
+
+
 def align(ref_seqs, qry_seqs, stage_limit=3, **kw):
     """Run the oracle.  Returns dict with
     mems     int64 [n,5]  q, strand, s1 (global ref pos), s2, len     sorted (q, strand, s2, s1)
@@ -76,9 +115,14 @@ def align(ref_seqs, qry_seqs, stage_limit=3, **kw):
     """
     L = lib()
     P = make_params(**kw)
-    rb, roff = _concat(ref_seqs)
     qb, qoff = _concat(qry_seqs)
-    h = L.orc_run(rb, roff.ctypes.data, len(ref_seqs), qb, qoff.ctypes.data, len(qry_seqs), ctypes.byref(P), stage_limit)
+    if isinstance(ref_seqs, Ref):
+        h = L.orc_run_ix(ref_seqs.h, qb, qoff.ctypes.data, len(qry_seqs), ctypes.byref(P), stage_limit)
+        if not h:
+            raise ValueError("the shared reference index was built for a larger minmatch")
+    else:
+        rb, roff = _concat(ref_seqs)
+        h = L.orc_run(rb, roff.ctypes.data, len(ref_seqs), qb, qoff.ctypes.data, len(qry_seqs), ctypes.byref(P), stage_limit)
     try:
         out = {}
         n = L.orc_n_mems(h)
@@ -96,9 +140,9 @@ def align(ref_seqs, qry_seqs, stage_limit=3, **kw):
         L.orc_get_rows(h, rows.ctypes.data, deltas.ctypes.data)
         out["rows"] = rows
         out["deltas"] = deltas
-        st = np.zeros(3, dtype=np.int64)
+        st = np.zeros(4, dtype=np.int64)
         L.orc_get_stats(h, st.ctypes.data)
-        out["stats"] = dict(cells=int(st[0]), max_band=int(st[1]), dp_calls=int(st[2]))
+        out["stats"] = dict(cells=int(st[0]), max_band=int(st[1]), dp_calls=int(st[2]), cap_hits=int(st[3]))
         return out
     finally:
         L.orc_free(h)

@@ -150,10 +150,13 @@ def test_large_mode_order(emu_engine, oracle, tmp_path):
     alignerRobot.set_engine(emu_engine)
     folder, d, reads = make_folder(tmp_path, n_reads=60)
     houseKeeper.globalLarge = True
+    cwd = os.getcwd()
+    os.chdir(folder)
     try:
         alignerRobot.useMummerAlignBatch("", folder, [["big", "LC_filtered.fasta", "SR.fasta", "big"]], 4)
     finally:
         houseKeeper.globalLarge = False
+        os.chdir(cwd)
     rows = alignerRobot.extractMumData(folder, "bigOut")
     o = oracle.align(d["contigs"], reads, band_cap=248)
     want = oracle.coords_rows(o["rows"], ["Segkk0", "Segkk1"], datagen.names("Segkk", len(reads)))
@@ -177,3 +180,174 @@ def test_batch_over_two_devices_emu(emu_engine, oracle, tmp_path):
         assert open(folder + "par" + idx + "Out").read().split("\n")[1:] == open(folder + "serial" + idx + "Out").read().split("\n")[1:]
         assert open(folder + "par" + idx + ".delta").read().split("\n")[1:] == open(folder + "serial" + idx + ".delta").read().split("\n")[1:]
     alignerRobot.set_engine(None)
+
+
+def test_large_mode_tile_order(emu_engine, oracle, tmp_path):
+    """globalLarge (alignerRobot.py:168-236): the coords file is the concatenation over reference part i = 1..10, query part
+    j = 1..10 of `show-coords -r` of tile (i, j) -- the ORDER is asserted, tile by tile, against the oracle run on the part
+    files the Perl splitter rule produces."""
+    alignerRobot.set_engine(emu_engine)
+    d = datagen.abun_gap(G=30_000, repeat_len=900, L=2500, seed=9)
+    folder = str(tmp_path) + "/"
+    # twelve reference records, so that the ten reference parts are not trivial
+    contigs = []
+    for c in d["contigs"]:
+        contigs += [c[i:i + 5000] for i in range(0, len(c), 5000)]
+    cnames = ["ctg%d" % i for i in range(len(contigs))]
+    reads = d["reads"][:70]
+    rnames = datagen.names("Segkk", len(reads))
+    fasta.write_fasta(folder + "ref.fasta", cnames, contigs)
+    fasta.write_fasta(folder + "qry.fasta", rnames, reads)
+    houseKeeper.globalLarge = True
+    cwd = os.getcwd()
+    os.chdir(folder)                       # fasta-splitter.pl writes the parts into the CWD and the tiles are read from there
+    try:
+        alignerRobot.useMummerAlignBatch("", folder, [["big", "ref.fasta", "qry.fasta", "big"]], 4)
+    finally:
+        houseKeeper.globalLarge = False
+        os.chdir(cwd)
+    rows = alignerRobot.extractMumData(folder, "bigOut")
+    assert os.path.exists(folder + "big0101.delta") and os.path.exists(folder + "ref.part-01.fasta")
+    want = []
+    rb = fasta.part_boundaries(cnames, contigs, 10)
+    qb = fasta.part_boundaries(rnames, reads, 10)
+    assert len(rb) > 3 and len(qb) > 3
+    for (r0, r1) in rb:
+        for (q0, q1) in qb:
+            o = oracle.align(contigs[r0:r1], reads[q0:q1], band_cap=248)
+            want += oracle.coords_rows(o["rows"], cnames[r0:r1], rnames[q0:q1])
+    assert len(want) > 20 and rows == want
+    alignerRobot.set_engine(None)
+
+
+def test_combine_and_special_for_raw(emu_engine, oracle, tmp_path):
+    """combineMultipleCoorMum (alignerRobot.py:74-96) and the specialForRaw=True call shape of gapFiller.formRelatedReadsFile
+    (gapFiller.py:116-182: reference = 4 x 400-base contig ends, query = read parts addressed by BARE path, coords written to
+    <folder><specialName>NN and then joined), followed by gapFiller's own inline parser and its `S1 < 10 and E1 > 390` rule."""
+    alignerRobot.set_engine(emu_engine)
+    folder, d, reads = make_folder(tmp_path, n_reads=90)
+    trunc, tnames = [], []
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for i, c in enumerate(d["contigs"]):
+        trunc += [c[:400], c[-400:], c[:400].translate(comp)[::-1], c[-400:].translate(comp)[::-1]]
+        tnames += ["Segkk%d_%s" % (i, t) for t in ("ph", "pt", "dh", "dt")]
+    fasta.write_fasta(folder + "improved3Trunc.fasta", tnames, trunc)
+    # reads that run over the contig ends (noisy copies of the first / last 2.5 kb at several offsets), both strands
+    rng = np.random.default_rng(17)
+    ends = []
+    for c in d["contigs"]:
+        g = np.frombuffer(c, dtype=np.uint8)
+        for off in (0, 3, 9, 12, 150, 395):
+            for piece in (g[off:off + 2500], g[len(g) - 2500 - off:len(g) - off]):
+                r, _ = datagen.noisy_reads(piece, 1, 2500, 0.01, 0.01, rng)
+                ends.append(r[0] if len(ends) % 2 else r[0].translate(comp)[::-1])
+    reads = reads[:40] + ends
+    fasta.write_fasta(folder + "SR.fasta", datagen.names("Segkk", len(reads)), reads)
+    n_parts = 5
+    paths = fasta.split_fasta(folder + "SR.fasta", n_parts, out_dir=folder)
+    raw_dir = str(tmp_path) + "/"                     # gapFiller passes the raw read parts with their own (bare) path
+    workerList = []
+    for i in range(1, n_parts + 1):
+        idx = alignerRobot.zeropadding(i)
+        workerList.append(["outGapFillRaw" + idx, "improved3Trunc.fasta", raw_dir + "SR.part-" + str(i) + ".fasta", "fromMumRaw" + idx])
+    alignerRobot.useMummerAlignBatch("", folder, workerList, 2, specialForRaw=True)
+    for i in range(1, n_parts + 1):
+        assert os.path.exists(folder + "fromMumRaw" + alignerRobot.zeropadding(i))
+        assert not os.path.exists(folder + "outGapFillRaw" + alignerRobot.zeropadding(i) + "Out")
+    alignerRobot.combineMultipleCoorMum(True, "", folder, "outGapFillRaw", "fromMumRaw", n_parts)
+    joined = open(folder + "fromMumRaw").read().split("\n")
+    want_rows, texts = [], []
+    for i, pth in enumerate(paths, start=1):
+        names, seqs = fasta.read_fasta(pth)
+        o = oracle.align(trunc, seqs, band_cap=248)
+        want_rows += oracle.coords_rows(o["rows"], tnames, names)
+        texts.append(oracle.coords_text(o["rows"], tnames, names, folder + "improved3Trunc.fasta", pth))
+    # head -5 of part 01, then tail -n+6 of every part
+    assert joined[1:5] == texts[0].split("\n")[1:5]
+    body = []
+    for t in texts:
+        body += t.split("\n")[5:-1]
+    assert joined[5:-1] == body and len(body) > 10
+    assert alignerRobot.extractMumData(folder, "fromMumRaw") == want_rows
+    # gapFiller.py:151-182: its own parser over every per-part file keeps the reads spanning a whole 400-base end
+    kept = []
+    endThres, thres = 10, 400
+    for i in range(1, n_parts + 1):
+        with open(folder + "fromMumRaw" + alignerRobot.zeropadding(i)) as f:
+            for _ in range(6):
+                tmp = f.readline()
+            while len(tmp) > 0:
+                infoArr = tmp.split("|")
+                rdGpArr = infoArr[-1].split("\t")
+                contigName, readName = rdGpArr[0].rstrip().lstrip(), rdGpArr[1].rstrip().lstrip()
+                pos = [int(x) for x in infoArr[0].split(" ") if len(x) > 0]
+                if pos[0] < endThres and pos[1] > thres - endThres:
+                    kept.append((contigName, readName))
+                tmp = f.readline()
+    want_kept = [(r[7], r[8]) for r in want_rows if r[0] < 10 and r[1] > 390]
+    assert kept == want_kept and len(kept) > 5
+    alignerRobot.set_engine(None)
+
+
+def test_refined_special_for_raw(emu_engine, oracle, tmp_path):
+    """The `-l 10` refine shape of abunSplitter.evaluateCoverage (abunSplitter.py:318-342): refinedVersion=True together with
+    specialForRaw=True, query parts by bare path."""
+    alignerRobot.set_engine(emu_engine)
+    folder, d, reads = make_folder(tmp_path, n_reads=30)
+    paths = fasta.split_fasta(folder + "SR.fasta", 3, out_dir=folder)
+    workerList = [["refine" + alignerRobot.zeropadding(i), "LC_filtered.fasta", p, "refineOut" + alignerRobot.zeropadding(i)] for i, p in enumerate(paths, start=1)]
+    alignerRobot.useMummerAlignBatch("", folder, workerList, 2, specialForRaw=True, refinedVersion=True)
+    got, want = [], []
+    for i, p in enumerate(paths, start=1):
+        got += alignerRobot.extractMumData(folder, "refineOut" + alignerRobot.zeropadding(i))
+        names, seqs = fasta.read_fasta(p)
+        o = oracle.align(d["contigs"], seqs, band_cap=248, minmatch=10)
+        want += oracle.coords_rows(o["rows"], ["Segkk0", "Segkk1"], names)
+    assert got == want and len(got) > 0
+    alignerRobot.set_engine(None)
+
+
+def test_index_cache_is_keyed_on_content(emu_engine, tmp_path):
+    """IORobot.alignWithName rewrites <name>leftSeg.fasta in place with the same size; with a coarse mtime the second call must
+    not be served the first call's index (regression: cache keyed on path/mtime/size)."""
+    alignerRobot.set_engine(emu_engine)
+    folder = str(tmp_path) + "/"
+    rng = np.random.default_rng(3)
+    a = datagen.random_genome(3000, rng).tobytes().decode()
+    b = datagen.random_genome(3000, rng).tobytes().decode()
+    real_stat = os.stat
+
+    def run(left, right):
+        out = IORobot.alignWithName(left, right, folder, "", "ov")
+        for f in ("ovleftSeg.fasta", "ovrightSeg.fasta"):
+            os.utime(folder + f, ns=(10**18, 10**18))          # pin the time stamps: same path, same size, same mtime
+        return out
+    assert run(a, a[2500:] + b[:2500]) == [500, 500]
+    assert run(b, b[2500:] + a[:2500]) == [500, 500]
+    assert run(a, b) == [0, 0]
+    assert real_stat is os.stat
+    alignerRobot.set_engine(None)
+
+
+def test_write_double_and_reverse_complement(tmp_path):
+    """IORobot.writeToFile_Double1 (IORobot.py:107-140) and houseKeeper.reverseComplement (houseKeeper.py:106-126) against a
+    character-by-character restatement."""
+    folder = str(tmp_path) + "/"
+    rng = np.random.default_rng(2)
+    seqs = [datagen.random_genome(n, rng).tobytes().decode() for n in (1, 59, 60, 61, 500)]
+    seqs[1] = seqs[1][:10] + "NnacgtX" + seqs[1][10:]
+    with open(folder + "in.fasta", "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">r%d extra words\n" % i)
+            for k in range(0, len(s), 60):
+                f.write(s[k:k + 60] + "\n")
+        f.write("\n>after_blank\nACGT\n")
+
+    def rc_ref(s):
+        m = {"A": "T", "a": "T", "T": "A", "t": "A", "C": "G", "c": "G", "G": "C", "g": "C", "N": "N", "n": "N"}
+        return "".join(m.get(ch, "") for ch in s[::-1])
+    for option, hdr in (("contig", ">Contig"), ("read", ">Read")):
+        IORobot.writeToFile_Double1(folder, "in.fasta", "out.fasta", option)
+        want = "".join("%s%d_p\n%s\n%s%d_d\n%s\n" % (hdr, i, s, hdr, i, rc_ref(s)) for i, s in enumerate(seqs))
+        assert open(folder + "out.fasta").read() == want
+    assert IORobot.reverseComplement("ACGTNacgtnX") == rc_ref("ACGTNacgtnX")
