@@ -78,7 +78,8 @@ int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_re
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]);
 /* ptr/bytes[5]: packed text, invalid mask, bucket heads, positions, bucket occupancy bitmap */
 int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]);
-int mfsc_index_build_ms(const mfsc_index* ix, double* ms);
+/* ms[0]: the whole build call (upload, packing, tables); ms[1]: the table kernels alone (count, scan, fill, occupancy) */
+int mfsc_index_build_ms(const mfsc_index* ix, double ms[2]);
 int mfsc_index_free(mfsc_index* ix);
 
 /* Index replication over the GPUs of one box (the reference's analogue is the fan-out of its 20 jobs over
@@ -137,7 +138,8 @@ int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand,
  * indel (positive: reference base without partner, negative: read base without partner) */
 int mfsc_result_deltas(const mfsc_result* r, int64_t* begin, int64_t* end, int32_t* deltas);
 /* stats[16]: 0 DP cells, 1 DP calls, 2 widest band, 3 probes, 4 matches, 5 kernel launches,
- * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes, 9 reads handed from the packed to the general DP engine;
+ * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes, 9 reads handed from the packed to the general DP engine,
+ * 10 anti-diagonals on which band_cap trimmed the band (0: the cap never bound, the rows are those of an uncapped DP);
  * ms[16]: 0 upload+pack, 1 seeds, 2 sort, 3 cluster, 4 extend, 5 compact+download, 6 total */
 int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]);
 int mfsc_result_free(mfsc_result* r);

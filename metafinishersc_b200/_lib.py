@@ -68,7 +68,7 @@ def bind(path):
     L.mfsc_index_create.argtypes = [c_vp, c_vp, c_i32, PP, c_i32, c_i64, ctypes.POINTER(c_vp)]
     L.mfsc_index_info.argtypes = [c_vp, c_vp]
     L.mfsc_index_buffers.argtypes = [c_vp, c_vp, c_vp]
-    L.mfsc_index_build_ms.argtypes = [c_vp, ctypes.POINTER(c_dbl)]
+    L.mfsc_index_build_ms.argtypes = [c_vp, c_vp]
     L.mfsc_index_free.argtypes = [c_vp]
     L.mfsc_comm_unique_id.argtypes = [c_vp]
     L.mfsc_comm_init_rank.argtypes = [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp)]

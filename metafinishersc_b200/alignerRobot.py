@@ -27,6 +27,31 @@ _CACHE_LOCK = threading.RLock()     # the GPU fan-out (_batch_on_gpus) touches t
 _INDEX_CACHE_MAX = 2
 _ROWS_CACHE_MAX = 64
 _HASH_WHOLE_BELOW = 64 << 20        # reference files up to this size are identified by a hash of all their bytes
+_QUERY_CACHE = {}      # query part path -> (names, bases, offsets) handed from largeRvsQAlign's splitter to the jobs in memory
+_WRITERS = None        # background threads for the text files (part FASTA, .delta, coords): the C writers release the GIL
+_PENDING = []          # futures of file writes not yet joined; every public entry point joins them before it returns
+
+
+def _submit(fn, *args):
+    """Run a file write on the writer pool (overlaps with the alignment of the next part)."""
+    global _WRITERS
+    if _WRITERS is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _WRITERS = ThreadPoolExecutor(max_workers=4)
+    f = _WRITERS.submit(fn, *args)
+    with _CACHE_LOCK:
+        _PENDING.append(f)
+    return f
+
+
+def _join_writes():
+    """All files of the calls so far are on disk when this returns (errors of the writers surface here)."""
+    while True:
+        with _CACHE_LOCK:
+            if not _PENDING:
+                return
+            f = _PENDING.pop(0)
+        f.result()
 fullDelta = True       # write real MUMmer delta records (indel offset lists); False: alignment headers only, ~25 % faster
 
 
@@ -75,6 +100,7 @@ def _stat_signature(path):
 
 
 def _rows_cache_put(delta, rs):
+    _PENDING_ROWS.pop(delta, None)
     with _CACHE_LOCK:
         while len(_ROWS_CACHE) >= _ROWS_CACHE_MAX and delta not in _ROWS_CACHE:
             _ROWS_CACHE.pop(next(iter(_ROWS_CACHE)), None)
@@ -116,16 +142,20 @@ class RowSet:
         return np.lexsort((np.arange(len(r)), r.s1, rr))
 
     def datalist(self):
-        """The list extractMumData would parse from the coords text (alignerRobot.py:34)."""
+        """The list extractMumData would parse from the coords text (alignerRobot.py:34).  Built from the row arrays in
+        bulk: %IDY is the single-precision show-coords value rounded to two decimals the way "%.2f" prints it (the float32
+        times 100 is exact in double precision, so rint / 100 is the correctly rounded decimal)."""
         r = self.rows
+        if len(r) == 0:
+            return []
         o = self.order()
-        idy = r.idy()
-        out = []
-        for i in o:
-            out.append([int(r.s1[i]), int(r.e1[i]), int(r.s2[i]), int(r.e2[i]), abs(int(r.e1[i]) - int(r.s1[i])) + 1,
-                        abs(int(r.e2[i]) - int(r.s2[i])) + 1, float("%.2f" % float(idy[i])), self.ref_names[r.ref_id[i]],
-                        self.qry_names[r.qry_id[i]]])
-        return out
+        s1, e1, s2, e2 = r.s1[o].astype(np.int64), r.e1[o].astype(np.int64), r.s2[o].astype(np.int64), r.e2[o].astype(np.int64)
+        idy = (np.rint(r.idy()[o].astype(np.float64) * 100.0) / 100.0).tolist()
+        rn, qn = self.ref_names, self.qry_names
+        rnames = [rn[i] for i in r.ref_id[o].tolist()]
+        qnames = [qn[i] for i in r.qry_id[o].tolist()]
+        return [list(t) for t in zip(s1.tolist(), e1.tolist(), s2.tolist(), e2.tolist(), (np.abs(e1 - s1) + 1).tolist(),
+                                     (np.abs(e2 - s2) + 1).tolist(), idy, rnames, qnames)]
 
 
 def _params(refinedVersion, maxmatch=True):
@@ -151,10 +181,12 @@ def _get_index(E, ref_path, params):
 
 
 def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
-    """One nucmer job: rows cached under `<prefix>.delta` and the delta file written."""
+    """One nucmer job: rows cached under `<prefix>.delta` and the delta file written (on the writer pool)."""
     E = E or get_engine()
     delta = prefix + ".delta"
-    if not (os.path.exists(ref_path) and os.path.exists(qry_path)):
+    with _CACHE_LOCK:
+        parsed = _QUERY_CACHE.get(os.path.abspath(qry_path))
+    if not (os.path.exists(ref_path) and (parsed is not None or os.path.exists(qry_path))):
         print("ERROR: Could not find input file(s) %s %s" % (ref_path, qry_path))   # nucmer's failure is ignored upstream too
         with _CACHE_LOCK:
             _ROWS_CACHE.pop(delta, None)
@@ -162,7 +194,7 @@ def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
             os.remove(delta)
         return None
     ix, rnames, rlens = index_entry if index_entry is not None else _get_index(E, ref_path, params)
-    qnames, qbuf, qoff = fasta.read_fasta_arrays(qry_path)
+    qnames, qbuf, qoff = parsed if parsed is not None else fasta.read_fasta_arrays(qry_path)
     qnames = [n.split()[0] if n.split() else n for n in qnames]
     try:
         rows = E.align(ix, (qbuf, qoff), params, flags=_engine_mod.WANT_DELTAS if fullDelta else 0)
@@ -172,20 +204,33 @@ def _run_nucmer(prefix, ref_path, qry_path, params, E=None, index_entry=None):
         print("note: delta lists did not fit for %s, writing alignment headers only (%s)" % (qry_path, err))
         rows = E.align(ix, (qbuf, qoff), params)
     rs = RowSet(rows, rnames, rlens, qnames, np.diff(qoff).tolist(), ref_path, qry_path)
-    E.write_delta(delta, rows, rnames, rlens, qnames, rs.qry_lens, os.path.abspath(ref_path), os.path.abspath(qry_path))
-    _rows_cache_put(delta, rs)
+    with _CACHE_LOCK:
+        _ROWS_CACHE.pop(delta, None)
+
+    def write():
+        E.write_delta(delta, rows, rnames, rlens, qnames, rs.qry_lens, os.path.abspath(ref_path), os.path.abspath(qry_path))
+        _rows_cache_put(delta, rs)
+    _PENDING_ROWS[delta] = rs          # served from here until the file is on disk
+    _submit(write)
     return rs
+
+
+_PENDING_ROWS = {}     # delta path -> RowSet whose delta file is still being written
 
 
 def nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion):
     """alignerRobot.py:46-64: `nucmer [-b 50 | -l 10] --maxmatch -p <folder><out> <folder><ref> <folder|''><qry>`."""
     qry = queryName if specialForRaw else folderName + queryName
-    return _run_nucmer(folderName + outputName, folderName + referenceName, qry, _params(refinedVersion))
+    rs = _run_nucmer(folderName + outputName, folderName + referenceName, qry, _params(refinedVersion))
+    _join_writes()
+    return rs
 
 
 def nucmerDefault(mummerLink, prefix, ref_path, qry_path):
     """The raw default-mode call of adaptorFix.py:21 (`nucmer -p <prefix> <ref> <qry>`, no --maxmatch)."""
-    return _run_nucmer(prefix, ref_path, qry_path, _params(False, maxmatch=False))
+    rs = _run_nucmer(prefix, ref_path, qry_path, _params(False, maxmatch=False))
+    _join_writes()
+    return rs
 
 
 def _load_delta(delta):
@@ -226,6 +271,9 @@ def _load_delta(delta):
 
 
 def _rowset_for(delta):
+    rs = _PENDING_ROWS.get(delta)
+    if rs is not None:
+        return rs
     rs = _rows_cache_get(delta)
     return rs if rs is not None else _load_delta(delta)
 
@@ -239,14 +287,28 @@ def _write_coords(rs, out_path):
 
 def showCoorMummer(specialForRaw, mummerLink, folderName, outputName, specialName):
     """alignerRobot.py:66-72: `show-coords -r <folder><out>.delta > <folder><out>Out | <folder><specialName>`."""
+    _join_writes()
     out = folderName + (specialName if specialForRaw else outputName + "Out")
     _write_coords(_rowset_for(folderName + outputName + ".delta"), out)
 
 
+def _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion, E=None, index_entry=None):
+    """nucmer + show-coords of one job without waiting for its files: the .delta and the coords table are formatted and
+    written on the writer pool while the caller goes on to the next job.  Callers join with _join_writes()."""
+    qry = queryName if specialForRaw else folderName + queryName
+    rs = _run_nucmer(folderName + outputName, folderName + referenceName, qry, _params(refinedVersion), E=E, index_entry=index_entry)
+    out = folderName + (specialName if specialForRaw else outputName + "Out")
+    if rs is None:
+        open(out, "w").close()
+    else:
+        _submit((E or get_engine()).write_coords, out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, True)
+    return rs
+
+
 def useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw=False, specialName="",
                    refinedVersion=False):
-    nucmerMummer(specialForRaw, mummerLink, folderName, outputName, referenceName, queryName, refinedVersion)
-    showCoorMummer(specialForRaw, mummerLink, folderName, outputName, specialName)
+    _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
+    _join_writes()
 
 
 def zeropadding(i):
@@ -276,7 +338,8 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
             _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, houseKeeper.globalGPUs)
             return
         for outputName, referenceName, queryName, specialName in workerList:
-            useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
+            _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
+        _join_writes()
         return
     # globalLarge (alignerRobot.py:168-236): reference and query are each split into 10 parts (written to the CWD, where
     # fasta-splitter.pl puts them), every (reference part i, query part j) tile is its own nucmer job
@@ -309,6 +372,7 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
                 lines += tl[5:]
         with open(out, "w") as f:
             f.writelines((header or []) + lines)
+    _join_writes()
 
 
 def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus):
@@ -347,12 +411,7 @@ def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus
                     qry_path = queryName if specialForRaw else folderName + queryName
                     rep = replicas.get(ref_path)
                     entry = (rep[0][slot], rep[1], rep[2]) if rep is not None else None
-                    rs = _run_nucmer(folderName + outputName, ref_path, qry_path, params, E=E, index_entry=entry)
-                    out = folderName + (specialName if specialForRaw else outputName + "Out")
-                    if rs is None:
-                        open(out, "w").close()
-                    else:
-                        E.write_coords(out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, sort_by_ref=True)
+                    _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion, E=E, index_entry=entry)
             except Exception as e:       # surfaced in the caller's thread
                 errors.append(e)
             finally:
@@ -364,6 +423,7 @@ def _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, n_gpus
             t.start()
         for t in threads:
             t.join()
+        _join_writes()
     finally:
         for per_dev, _, _ in replicas.values():
             for ix in per_dev[1:]:               # entry 0 is the cached index of the calling thread
@@ -403,17 +463,25 @@ def extractMumData(folderName, fileName):
 
 def largeRvsQAlign(folderName, numberOfFiles, mummerLink, refFile, qryFile, mumTmpHeader):
     """alignerRobot.py:258-297: split the query FASTA into parts, align every part against the reference,
-    return the concatenated rows of parts 01..NN (each part in show-coords -r order)."""
-    fasta.split_fasta(folderName + qryFile + ".fasta", numberOfFiles, out_dir=folderName)
-    numberOfFiles = houseKeeper.globalParallelFileNum      # the reference re-reads the global here (alignerRobot.py:271)
-    workerList = []
-    for i in range(1, numberOfFiles + 1):
-        idx = zeropadding(i)
-        workerList.append([mumTmpHeader + idx, refFile + ".fasta", qryFile + ".part-" + idx + ".fasta", mumTmpHeader + idx])
-    useMummerAlignBatch(mummerLink, folderName, workerList, houseKeeper.globalParallel, False)
+    return the concatenated rows of parts 01..NN (each part in show-coords -r order).
+    Pipeline: the query file is parsed once (a few host threads); the part files the rest of the reference pipeline
+    re-reads are written on the writer pool while the parts, handed over in memory, are aligned one after the other on
+    the GPU; the .delta and coords text of part i is formatted and written while part i+1 is aligned."""
+    parts = fasta.split_fasta(folderName + qryFile + ".fasta", numberOfFiles, out_dir=folderName, submit=_submit, keep=_QUERY_CACHE)
+    try:
+        numberOfFiles = houseKeeper.globalParallelFileNum      # the reference re-reads the global here (alignerRobot.py:271)
+        workerList = []
+        for i in range(1, numberOfFiles + 1):
+            idx = zeropadding(i)
+            workerList.append([mumTmpHeader + idx, refFile + ".fasta", qryFile + ".part-" + idx + ".fasta", mumTmpHeader + idx])
+        useMummerAlignBatch(mummerLink, folderName, workerList, houseKeeper.globalParallel, False)
+    finally:
+        with _CACHE_LOCK:
+            for p in parts:
+                _QUERY_CACHE.pop(os.path.abspath(p), None)
     dataList = []
     for i in range(1, numberOfFiles + 1):
         rs = _rows_cache_get(folderName + mumTmpHeader + zeropadding(i) + ".delta")
         # rows served from memory when this process produced them; identical to parsing the text
-        dataList = dataList + (rs.datalist() if rs is not None else extractMumData(folderName, mumTmpHeader + zeropadding(i) + "Out"))
+        dataList += rs.datalist() if rs is not None else extractMumData(folderName, mumTmpHeader + zeropadding(i) + "Out")
     return dataList

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef MFSC_EMU
@@ -74,7 +75,12 @@ struct Dev {
     return p;
   }
   void free_(void* p) { if (p) cudaFreeAsync(p, stream); }
-  void h2d(void* d, const void* h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream); }
+  // large uploads go in 32 MB pieces: the copy engine arbitrates between streams per operation, so a small upload of another
+  // stream (the contigs of an index build next to a 1.5 GB read batch) waits for one piece, not for the whole batch
+  void h2d(void* d, const void* h, size_t n) {
+    const size_t piece = (size_t)32 << 20;
+    for (size_t o = 0; o < n; o += piece) cudaMemcpyAsync((char*)d + o, (const char*)h + o, n - o < piece ? n - o : piece, cudaMemcpyHostToDevice, stream);
+  }
   void d2h(void* h, const void* d, size_t n) { if (n) { cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); } }
   void zero(void* d, size_t n) { if (n) cudaMemsetAsync(d, 0, n, stream); }
   void sync() { cudaStreamSynchronize(stream); }
@@ -295,7 +301,7 @@ struct mfsc_index {
   unsigned* H = nullptr; unsigned* pos = nullptr;
   unsigned* occ = nullptr;      // one bit per bucket: not empty
   int k = 0; long long n_buckets = 0, n_pos = 0;
-  double build_ms = 0;
+  double build_ms = 0, tables_ms = 0;   // whole mfsc_index_create call / the table kernels alone (count, scan, fill, occupancy)
   int device = -1;              // device the buffers live on
   bool plain = false;           // buffers come from cudaMalloc (replicas made by mfsc_index_broadcast), not from the stream-ordered pool
 };
@@ -444,6 +450,8 @@ int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_re
   ix->occ = dalloc<unsigned>(D, ix->n_buckets / 32 + 2);
   if (!ix->H || !ix->ostart || !ix->occ) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (bucket table)"); }
   D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
+  Stamp tk;
+  stamp(D, tk);
   if (build_tables) {
     D.zero(ix->H, sizeof(unsigned) * (ix->n_buckets + 2));
     const unsigned g = grid_for(D, ix->ref.n_words, 256, 16);
@@ -465,7 +473,8 @@ int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_re
   stamp(D, t1);
   D.sync();
   ix->build_ms = elapsed_ms(D, t0, t1);
-  stamp_free(t0); stamp_free(t1);
+  ix->tables_ms = elapsed_ms(D, tk, t1);
+  stamp_free(t0); stamp_free(t1); stamp_free(tk);
   std::string msg;
   if (!dev_check(msg)) { index_release(D, ix); return fail(MFSC_ERR_CUDA, "index build: " + msg); }
   *out = ix;
@@ -494,7 +503,11 @@ int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]) {
   return MFSC_OK;
 }
 
-int mfsc_index_build_ms(const mfsc_index* ix, double* ms) { if (!ix) return fail(MFSC_ERR_ARG, "index is NULL"); *ms = ix->build_ms; return MFSC_OK; }
+int mfsc_index_build_ms(const mfsc_index* ix, double ms[2]) {
+  if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
+  ms[0] = ix->build_ms; ms[1] = ix->tables_ms;
+  return MFSC_OK;
+}
 
 int mfsc_index_free(mfsc_index* ix) {
   if (!ix) return MFSC_OK;
@@ -947,7 +960,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       I.seg = seg; I.n_pc = o_npc; I.pc_first = o_pcf; I.pc_n = o_pcn; I.pc_rec = o_pcr; I.cm_s1 = o_s1; I.cm_s2 = o_s2; I.cm_len = o_len;
       I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.grp = x_grp; I.fused = x_fused;
       I.list = nullptr; I.n_list = nullptr; I.retry = x_retry; I.n_retry = (unsigned*)(d_stats + 4);
-      ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2);
+      ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2); st.caps = d_stats + 5;
       const int ext_block = 128;
       const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
       const size_t pk_smem = (size_t)(ext_block / MFSC_LANES) * PK_SMEM_INTS * sizeof(int);
@@ -1051,6 +1064,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       unsigned long long hst[8];
       D.d2h(hst, d_stats, sizeof(hst));
       res->stats[9] = (int64_t)(hst[4] & 0xffffffffull);
+      res->stats[10] = (int64_t)hst[5];
       res->stats[0] = (int64_t)hst[0]; res->stats[1] = (int64_t)hst[1]; res->stats[2] = (int64_t)(int)(hst[2] & 0xffffffffull);
       res->stats[8] = n_rows * 32 + 8;
       stamp(D, ts[5]);
@@ -1382,31 +1396,75 @@ int mfsc_fasta_count(const uint8_t* data, int64_t n, int32_t* n_rec_out) {
   return MFSC_OK;
 }
 
-int mfsc_fasta_parse(const uint8_t* data, int64_t n, uint8_t* bases_out, int64_t* off_out, int64_t* name_span_out, int32_t max_rec,
-                     int32_t* n_rec_out) {
-  if (!data || n < 0 || !bases_out || !off_out || !name_span_out || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: bad arguments");
-  int32_t rec = 0; int64_t w = 0, i = 0;
-  off_out[0] = 0;
-  while (i < n) {
-    const void* nl = memchr(data + i, '\n', (size_t)(n - i));
-    const int64_t e = nl ? (const uint8_t*)nl - data : n;
-    int64_t le = e;
+// one chunk of a FASTA buffer that starts at a header line (or at byte 0): either counts its records and bases
+// (bases_out == nullptr) or writes them at the given record / base offsets
+static void fasta_chunk(const uint8_t* data, int64_t b, int64_t e, bool first_chunk, int64_t rec0, int64_t w0, uint8_t* bases_out, int64_t* off_out,
+                        int64_t* name_span_out, int64_t* n_rec, int64_t* n_bases) {
+  int64_t rec = 0, w = w0, i = b;
+  bool in_rec = !first_chunk;   // later chunks begin with a header by construction
+  (void)in_rec;
+  bool seen = false;
+  while (i < e) {
+    const void* nl = memchr(data + i, '\n', (size_t)(e - i));
+    const int64_t le0 = nl ? (const uint8_t*)nl - data : e;
+    int64_t le = le0;
     while (le > i && (data[le - 1] == '\r')) le--;
     if (le > i) {
       if (data[i] == '>') {
-        if (rec >= max_rec) { int32_t c = 0; mfsc_fasta_count(data, n, &c); *n_rec_out = c; return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: more records than max_rec"); }
-        if (rec > 0) off_out[rec] = w;
-        name_span_out[2 * rec] = i + 1; name_span_out[2 * rec + 1] = le;
-        rec++;
-      } else if (rec > 0) {
-        memcpy(bases_out + w, data + i, (size_t)(le - i));
+        if (bases_out) { off_out[rec0 + rec] = w; name_span_out[2 * (rec0 + rec)] = i + 1; name_span_out[2 * (rec0 + rec) + 1] = le; }
+        rec++; seen = true;
+      } else if (seen) {
+        if (bases_out) memcpy(bases_out + w, data + i, (size_t)(le - i));
         w += le - i;
       }
     }
-    i = e + 1;
+    i = le0 + 1;
   }
+  *n_rec = rec; *n_bases = w - w0;
+}
+
+int mfsc_fasta_parse(const uint8_t* data, int64_t n, uint8_t* bases_out, int64_t* off_out, int64_t* name_span_out, int32_t max_rec,
+                     int32_t* n_rec_out) {
+  if (!data || n < 0 || !bases_out || !off_out || !name_span_out || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: bad arguments");
+  // chunks that begin at header lines, parsed by a few host threads: count, prefix sums, copy
+  int T = 1;
+  if (n > (int64_t)(8 << 20)) { T = (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())); }
+  std::vector<int64_t> cb(1, 0);
+  for (int t = 1; t < T; t++) {
+    int64_t p = n * t / T;
+    if (p <= cb.back()) continue;
+    // next "\n>" at or after p
+    while (p < n) {
+      const void* nl = memchr(data + p, '\n', (size_t)(n - p));
+      if (!nl) { p = n; break; }
+      p = (const uint8_t*)nl - data + 1;
+      if (p < n && data[p] == '>') break;
+    }
+    if (p < n && p > cb.back()) cb.push_back(p);
+  }
+  cb.push_back(n);
+  const int C = (int)cb.size() - 1;
+  std::vector<int64_t> cr(C, 0), cw(C, 0);
+  {
+    std::vector<std::thread> th;
+    for (int c = 1; c < C; c++) th.emplace_back([&, c]() { fasta_chunk(data, cb[c], cb[c + 1], false, 0, 0, nullptr, nullptr, nullptr, &cr[c], &cw[c]); });
+    fasta_chunk(data, cb[0], cb[1], true, 0, 0, nullptr, nullptr, nullptr, &cr[0], &cw[0]);
+    for (auto& x : th) x.join();
+  }
+  int64_t rec = 0, w = 0;
+  std::vector<int64_t> r0(C), w0(C);
+  for (int c = 0; c < C; c++) { r0[c] = rec; w0[c] = w; rec += cr[c]; w += cw[c]; }
+  if (rec > max_rec) { *n_rec_out = (int32_t)rec; return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: more records than max_rec"); }
+  {
+    std::vector<std::thread> th;
+    int64_t dr, dw;
+    for (int c = 1; c < C; c++) th.emplace_back([&, c]() { int64_t a, b2; fasta_chunk(data, cb[c], cb[c + 1], false, r0[c], w0[c], bases_out, off_out, name_span_out, &a, &b2); });
+    fasta_chunk(data, cb[0], cb[1], true, r0[0], w0[0], bases_out, off_out, name_span_out, &dr, &dw);
+    for (auto& x : th) x.join();
+  }
+  if (rec == 0) off_out[0] = 0;
   off_out[rec] = w;
-  *n_rec_out = rec;
+  *n_rec_out = (int32_t)rec;
   return MFSC_OK;
 }
 
@@ -1415,16 +1473,27 @@ int mfsc_fasta_write(const char* path, const char* names, const int64_t* name_of
   if (!path || !names || !name_off || !bases || !off || rec_begin < 0 || rec_end < rec_begin) return fail(MFSC_ERR_ARG, "mfsc_fasta_write: bad arguments");
   FILE* f = fopen(path, "wb");
   if (!f) return fail(MFSC_ERR_IO, std::string("cannot open ") + path);
-  std::vector<char> buf(1 << 20);
-  setvbuf(f, buf.data(), _IOFBF, buf.size());
+  // formatted by hand into a block buffer (a wrapped 10 kb read is 167 lines: no stdio call per line)
+  std::vector<char> buf((size_t)4 << 20);
+  size_t w = 0;
+  auto flush = [&](size_t need) { if (w + need > buf.size()) { fwrite(buf.data(), 1, w, f); w = 0; } };
   for (int32_t r = rec_begin; r < rec_end; r++) {
-    fputc('>', f);
-    fwrite(names + name_off[r], 1, (size_t)(name_off[r + 1] - name_off[r]), f);
-    fputc('\n', f);
+    const size_t nl = (size_t)(name_off[r + 1] - name_off[r]);
+    if (nl + 2 > buf.size()) { fwrite(buf.data(), 1, w, f); w = 0; fputc('>', f); fwrite(names + name_off[r], 1, nl, f); fputc('\n', f); }
+    else { flush(nl + 2); buf[w++] = '>'; memcpy(&buf[w], names + name_off[r], nl); w += nl; buf[w++] = '\n'; }
     const int64_t b = off[r], e = off[r + 1];
-    if (line_len <= 0) { fwrite(bases + b, 1, (size_t)(e - b), f); fputc('\n', f); }
-    else for (int64_t p = b; p < e; p += line_len) { fwrite(bases + p, 1, (size_t)std::min<int64_t>(line_len, e - p), f); fputc('\n', f); }
+    if (line_len <= 0) {
+      if ((size_t)(e - b) + 1 > buf.size()) { fwrite(buf.data(), 1, w, f); w = 0; fwrite(bases + b, 1, (size_t)(e - b), f); fputc('\n', f); }
+      else { flush((size_t)(e - b) + 1); memcpy(&buf[w], bases + b, (size_t)(e - b)); w += (size_t)(e - b); buf[w++] = '\n'; }
+    } else {
+      for (int64_t p = b; p < e; p += line_len) {
+        const size_t m = (size_t)std::min<int64_t>(line_len, e - p);
+        flush(m + 1);
+        memcpy(&buf[w], bases + p, m); w += m; buf[w++] = '\n';
+      }
+    }
   }
+  fwrite(buf.data(), 1, w, f);
   fclose(f);
   return MFSC_OK;
 }

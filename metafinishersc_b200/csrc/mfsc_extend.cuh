@@ -41,7 +41,7 @@
 
 struct DpOut { int reached, fi, fj, cols, errs, n_ops; };
 
-struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max_band; };
+struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max_band; unsigned long long* caps; };   // caps: anti-diagonals on which band_cap trimmed the band
 
 // View of one sequence: 1-based position i lives at padded position base + i - 1
 struct SeqView { unsigned base; int n; };
@@ -69,7 +69,7 @@ struct DeltaOut { int* buf; unsigned long long* used; long long cap; unsigned* n
 
 struct ExtCtx {
   SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
-  mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw;   // per-warp statistics, flushed once per kernel
+  mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw, acc_caps;   // per-warp statistics, flushed once per kernel
   mutable TbCtx T;
   mutable int pk_fail;           // packed engine only: a field did not fit, the read goes to the general engine
   SeqView A; SeqView B[2];
@@ -364,6 +364,7 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
       int l2 = lo, h2 = hi;
       while (l2 <= h2 && h2 - l2 + 2 > band_cap) { if (cB[l2 & DP_SMASK] < cB[h2 & DP_SMASK]) l2++; else h2--; }
       lo = wmax_i32(l2); hi = wmax_i32(h2);      // values read from memory: hand them back as uniform
+      if (lane == 0) E.acc_caps++;
     }
     {
       const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;
@@ -663,7 +664,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * (PK ? PK_SMEM_INTS : DP_SMEM_INTS);
 #endif
   const int lane = lane_id();
-  unsigned long long w_cells = 0, w_calls = 0; int w_maxw = 0;
+  unsigned long long w_cells = 0, w_calls = 0, w_caps = 0; int w_maxw = 0;
   const int n_work = I.list ? (int)*I.n_list : n_reads;
   // reads are handed out by a ticket counter: a warp takes the next read when it is done with its own
   for (;;) {
@@ -716,7 +717,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     wsync();
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
-    E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0;
+    E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0; E.acc_caps = 0;
     E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.cap = 0; E.T.top = 0; E.T.bad = 0;
     E.pk_fail = 0;
     if (TB) {
@@ -769,12 +770,13 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
       }
       wsync();
     }
-    w_cells += E.acc_cells; w_calls += E.acc_calls; if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
+    w_cells += E.acc_cells; w_calls += E.acc_calls; w_caps += (unsigned long long)E.acc_caps; if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
   }
   if (lane == 0 && w_calls) {
     atomic_add_u64(st.cells, w_cells);
     atomic_add_u64(st.calls, w_calls);
     atomic_max_i32(st.max_band, w_maxw);
+    if (w_caps) atomic_add_u64(st.caps, w_caps);
   }
 }
 

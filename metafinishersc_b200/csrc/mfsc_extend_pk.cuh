@@ -376,6 +376,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
       int l2 = lo, h2 = hi;
       while (l2 <= h2 && h2 - l2 + 2 > band_cap) { if ((cB[l2 & DP_SMASK] & PK_SCORE) < (cB[h2 & DP_SMASK] & PK_SCORE)) l2++; else h2--; }
       lo = wmax_i32(l2); hi = wmax_i32(h2);
+      if (lane == 0) E.acc_caps++;
     }
     if ((d & (PK_PERIOD - 1)) == 0) {
       // Rebase the live words: what this diagonal wrote (nD, nI, its best buffer over [nlo, nhi]) and the best buffer

@@ -107,11 +107,13 @@ def part_boundaries_len(name_lens, seq_lens, n_parts, line_len=60):
     return parts
 
 
-def split_fasta(path, n_parts, out_dir=None, line_len=60):
+def split_fasta(path, n_parts, out_dir=None, line_len=60, submit=None, keep=None):
     """Write <base>.part-NN.fasta files; returns their paths.  fasta-splitter.pl writes into
     the CWD and alignerRobot.py:268-269 then copies them into the folder; callers pass
     out_dir=folder to land them there directly.  Parsing and the wrapped part files are done in C
-    (mfsc_fasta_parse / mfsc_fasta_write); the part boundaries follow the Perl script."""
+    (mfsc_fasta_parse / mfsc_fasta_write); the part boundaries follow the Perl script.
+    submit(fn, *args): when given, the part files are written through it (a background pool) instead of inline;
+    keep: dict that receives abspath(part) -> (names, bases, offsets) of every part, views into the parsed arrays."""
     from . import _lib
     L = _lib.load()
     names, bases, off = read_fasta_arrays(path)
@@ -134,7 +136,14 @@ def split_fasta(path, n_parts, out_dir=None, line_len=60):
     for p, (b, e) in enumerate(bounds, start=1):
         stem = base if (".part-" in base and base.rsplit(".part-", 1)[1].isdigit()) else base + ".part"
         out = os.path.join(out_dir, "%s-%0*d%s" % (stem, num_len, p, ext))
-        _lib.check(L, L.mfsc_fasta_write(out.encode(), blob, _lib.ptr(name_off), _lib.ptr(bases) if bases.size else _lib.ptr(np.zeros(1, np.uint8)),
-                                         _lib.ptr(off), b, e, line_len))
+        def write(out=out, b=b, e=e):
+            _lib.check(L, L.mfsc_fasta_write(out.encode(), blob, _lib.ptr(name_off), _lib.ptr(bases) if bases.size else _lib.ptr(np.zeros(1, np.uint8)),
+                                             _lib.ptr(off), b, e, line_len))
+        if submit is not None:
+            submit(write)
+        else:
+            write()
+        if keep is not None:
+            keep[os.path.abspath(out)] = (names[b:e], bases[off[b]:off[e]], off[b:e + 1] - off[b])
         paths.append(out)
     return paths

@@ -99,6 +99,9 @@ def run_case(E, O, ref, qry, opts):
                    got[first].tolist() if first < len(got) else None, want[first].tolist() if first < len(want) else None))
     if len(r) and r.stats["cells"] != o["stats"]["cells"]:
         bad.append("DP cells differ: %d vs %d" % (r.stats["cells"], o["stats"]["cells"]))
+    if len(r) and (r.stats["cap_hits"] != o["stats"]["cap_hits"] or r.stats["max_band"] != o["stats"]["max_band"]):
+        bad.append("band statistics differ: cap hits %d vs %d, widest band %d vs %d" % (r.stats["cap_hits"], o["stats"]["cap_hits"],
+                                                                                      r.stats["max_band"], o["stats"]["max_band"]))
     # delta mode: same rows, plus the indel offset list of every row bit-exact
     ix = E.index(ref, P)
     rd = E.align(ix, qry, P, flags=engine.WANT_DELTAS)
