@@ -601,8 +601,9 @@ def main():
                                       "(Q query bases of both strands, P probes, M matches)"),
             "roofline_cluster": hbm_line("k_cluster", 16 * M + 12 * M, clu_ms, "16 B per match read + 12 B per cluster match written; the kernel is bound "
                                          "by the serial mgaps rules per strand (lanes active, see profiles/), not by bytes"),
-            "roofline_index": hbm_line("k_index_*", R_bases // 4 * 2 + 4 * info["positions"] + 8 * (info["buckets"]), tables_ms,
-                                       "stage 1 tables: 0.25 R read twice (count, fill) + 4 R positions written + 8 x 4^k bucket heads (zero + scan)"),
+            "roofline_index": hbm_line("k_index_*", R_bases // 4 * 2 + 4 * info["positions"] + 8 * (4 ** info["k"]), tables_ms,
+                                       "stage 1 tables: 0.25 R read twice (count, fill) + 4 R positions written + 8 x 4^k for the dense scratch histogram "
+                                       "(zero + scan) that the compact directory + heads are made from"),
             "roofline_coverage": hbm_line("k_cov_*", cov_bytes, cov_ms, "stage 5 over this step's rows: 8 N_rows + 12 C (difference array written, "
                                           "read, profile written)") if cov_ms else None,
             "strong": strong,

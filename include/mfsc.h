@@ -71,12 +71,12 @@ int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec
 /* Replication over several GPUs: the root rank builds the index; every other rank creates an empty one of the
  * same shape (`build_tables` = 0, `p->kmer` and `n_positions` taken from the root's mfsc_index_info, `bases` may be
  * NULL), then all ranks fetch the device buffers with mfsc_index_buffers and broadcast them (NCCL through
- * torch.distributed, one call per buffer).  info: [0] k, [1] device, [2] text words, [3] buckets+2, [4] positions,
+ * torch.distributed, one call per buffer).  info: [0] k, [1] device, [2] text words, [3] occupied buckets, [4] positions,
  * [5] bytes in HBM, [6] records, [7] bases. */
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                       int32_t build_tables, int64_t n_positions, mfsc_index** out);
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]);
-/* ptr/bytes[5]: packed text, invalid mask, bucket heads, positions, bucket occupancy bitmap */
+/* ptr/bytes[5]: packed text, invalid mask, bucket directory (8 B per 32 buckets), positions, heads of the occupied buckets */
 int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]);
 /* ms[0]: the whole build call (upload, packing, tables); ms[1]: the table kernels alone (count, scan, fill, occupancy) */
 int mfsc_index_build_ms(const mfsc_index* ix, double ms[2]);

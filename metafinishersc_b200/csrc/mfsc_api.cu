@@ -298,9 +298,11 @@ struct mfsc_index {
   SeqDev ref;
   unsigned* ostart = nullptr;   // separator-joined coordinate of each record
   std::vector<unsigned> h_ostart;
-  unsigned* H = nullptr; unsigned* pos = nullptr;
-  unsigned* occ = nullptr;      // one bit per bucket: not empty
-  int k = 0; long long n_buckets = 0, n_pos = 0;
+  uint2* dir = nullptr;         // [n_buckets / 32 + 1] {occupancy bits, occupied buckets before the word}  (mfsc_seq.cuh)
+  unsigned* heads = nullptr;    // [n_heads + 1] first position slot of every occupied bucket, then n_pos
+  unsigned* pos = nullptr;      // [n_pos] text positions grouped by bucket
+  int k = 0; long long n_buckets = 0, n_pos = 0, n_heads = 0;
+  KmerIndex view() const { KmerIndex X; X.dir = dir; X.heads = heads; X.pos = pos; return X; }
   double build_ms = 0, tables_ms = 0;   // whole mfsc_index_create call / the table kernels alone (count, scan, fill, occupancy)
   int device = -1;              // device the buffers live on
   bool plain = false;           // buffers come from cudaMalloc (replicas made by mfsc_index_broadcast), not from the stream-ordered pool
@@ -420,18 +422,65 @@ static void index_release(Dev& D, mfsc_index* ix) {
     // buffers of another device (or of a replica made with cudaMalloc): free them synchronously on their own device
     DeviceGuard g(ix->device);
     dev_free_plain(ix->ref.txt); dev_free_plain(ix->ref.inv); dev_free_plain(ix->ref.start); dev_free_plain(ix->ref.len);
-    dev_free_plain(ix->ostart); dev_free_plain(ix->H); dev_free_plain(ix->pos); dev_free_plain(ix->occ);
+    dev_free_plain(ix->ostart); dev_free_plain(ix->dir); dev_free_plain(ix->heads); dev_free_plain(ix->pos);
   } else {
     seq_free(D, ix->ref);
-    D.free_(ix->ostart); D.free_(ix->H); D.free_(ix->pos); D.free_(ix->occ);
+    D.free_(ix->ostart); D.free_(ix->dir); D.free_(ix->heads); D.free_(ix->pos);
   }
   delete ix;
 }
 
+// Tables of the bucket slice [b_lo, b_hi) of the k-mer space (both multiples of 32) from the packed text: a dense
+// histogram as scratch (zero, count, inclusive scan, fill), then the compact form -- directory words with ranks relative
+// to the slice, heads relative to the slice's own position array.
+struct TableSlice { uint2* dir = nullptr; unsigned* heads = nullptr; unsigned* pos = nullptr; long long n_words = 0, n_occ = 0, n_pos = 0; };
+
+static void slice_free(Dev& D, TableSlice& S) { D.free_(S.dir); D.free_(S.heads); D.free_(S.pos); S.dir = nullptr; S.heads = nullptr; S.pos = nullptr; }
+
+static bool build_slice(Dev& D, const SeqDev& ref, int k, unsigned long long b_lo, unsigned long long b_hi, TableSlice& S, std::string& err) {
+  const long long nb = (long long)(b_hi - b_lo);
+  S.n_words = nb / 32;
+  unsigned* H = dalloc<unsigned>(D, nb + 2);
+  unsigned* bits = dalloc<unsigned>(D, S.n_words + 1);
+  unsigned* cnt = dalloc<unsigned>(D, S.n_words + 2);
+  S.dir = dalloc<uint2>(D, S.n_words + 1);
+  auto scratch_free = [&]() { D.free_(H); D.free_(bits); D.free_(cnt); };
+  if (!H || !bits || !cnt || !S.dir) { scratch_free(); slice_free(D, S); err = "out of device memory (bucket histogram)"; return false; }
+  D.zero(H, sizeof(unsigned) * (nb + 2));
+  const unsigned g = grid_for(D, ref.n_words, 256, 16);
+  MFSC_LAUNCH(k_index_count, g, 256, 0, D.stream, ref.txt, ref.inv, ref.n_words, k, b_lo, b_hi, H);
+  if (!inclusive_sum_u32(D, H, nb + 2)) { scratch_free(); slice_free(D, S); err = "out of device memory (scan)"; return false; }
+  unsigned total = 0;
+  D.d2h(&total, H + nb + 1, sizeof(unsigned));
+  S.n_pos = total;
+  S.pos = dalloc<unsigned>(D, (size_t)total + 1);
+  if (!S.pos) { scratch_free(); slice_free(D, S); err = "out of device memory (position table)"; return false; }
+  MFSC_LAUNCH(k_index_fill, g, 256, 0, D.stream, ref.txt, ref.inv, ref.n_words, k, b_lo, b_hi, H, S.pos);
+  const unsigned gw = grid_for(D, S.n_words, 256, 16);
+  MFSC_LAUNCH(k_index_dir_bits, gw, 256, 0, D.stream, H, nb, bits, cnt);
+  D.zero(cnt + S.n_words, sizeof(unsigned));
+  // exclusive scan of the per-word counts = inclusive scan shifted by one word: scan in place, read the total, shift by using cnt - 1
+  if (!inclusive_sum_u32(D, cnt, S.n_words + 1)) { scratch_free(); slice_free(D, S); err = "out of device memory (scan)"; return false; }
+  unsigned occ = 0;
+  D.d2h(&occ, cnt + S.n_words, sizeof(unsigned));
+  S.n_occ = occ;
+  S.heads = dalloc<unsigned>(D, (size_t)occ + 2);
+  unsigned* rank = dalloc<unsigned>(D, S.n_words + 1);
+  if (!S.heads || !rank) { D.free_(rank); scratch_free(); slice_free(D, S); err = "out of device memory (bucket heads)"; return false; }
+  MFSC_LAUNCH(k_excl_from_incl, gw, 256, 0, D.stream, cnt, bits, S.n_words, rank);
+  MFSC_LAUNCH(k_index_heads, gw, 256, 0, D.stream, H, nb, bits, rank, 0u, 0u, S.dir, S.heads);
+  D.launches += 5;
+  D.sync();
+  D.free_(rank);
+  scratch_free();
+  return true;
+}
+
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p, int32_t build_tables,
                       int64_t n_positions, mfsc_index** out) {
-  if (!rec_off || n_rec <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_index_create: bad arguments");
-  if (build_tables && !bases) return fail(MFSC_ERR_ARG, "mfsc_index_create: bases is NULL");
+  (void)n_positions;
+  if (!rec_off || n_rec <= 0 || !out || !bases) return fail(MFSC_ERR_ARG, "mfsc_index_create: bad arguments");
+  if (!build_tables) return fail(MFSC_ERR_ARG, "mfsc_index_create: empty shells are no longer made here; replicas come from mfsc_index_broadcast");
   int rc = check_params(p); if (rc) return rc;
   Dev& D = g_dev;
   if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
@@ -440,35 +489,23 @@ int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_re
   std::string err;
   Stamp t0, t1;
   stamp(D, t0);
-  if (!seq_upload(D, bases, rec_off, n_rec, 0, build_tables != 0, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
+  if (!seq_upload(D, bases, rec_off, n_rec, 0, true, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
   ix->h_ostart.resize(n_rec);
   for (int r = 0; r < n_rec; r++) ix->h_ostart[r] = (unsigned)(rec_off[r] - rec_off[0] + r);
   ix->ostart = dalloc<unsigned>(D, n_rec);
   ix->k = choose_k(p, ix->ref.n_bases);
   ix->n_buckets = 1ll << (2 * ix->k);
-  ix->H = dalloc<unsigned>(D, ix->n_buckets + 2);
-  ix->occ = dalloc<unsigned>(D, ix->n_buckets / 32 + 2);
-  if (!ix->H || !ix->ostart || !ix->occ) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (bucket table)"); }
+  if (!ix->ostart) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (record table)"); }
   D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
   Stamp tk;
   stamp(D, tk);
-  if (build_tables) {
-    D.zero(ix->H, sizeof(unsigned) * (ix->n_buckets + 2));
-    const unsigned g = grid_for(D, ix->ref.n_words, 256, 16);
-    MFSC_LAUNCH(k_index_count, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H);
-    if (!inclusive_sum_u32(D, ix->H, ix->n_buckets + 2)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (scan)"); }
-    unsigned total = 0;
-    D.d2h(&total, ix->H + ix->n_buckets + 1, sizeof(unsigned));
-    ix->n_pos = total;
-    ix->pos = dalloc<unsigned>(D, (size_t)total + 1);
-    if (!ix->pos) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
-    MFSC_LAUNCH(k_index_fill, g, 256, 0, D.stream, ix->ref.txt, ix->ref.inv, ix->ref.n_words, ix->k, ix->H, ix->pos);
-    MFSC_LAUNCH(k_index_occ, grid_for(D, ix->n_buckets / 32 + 1, 256, 16), 256, 0, D.stream, ix->H, ix->n_buckets, ix->occ);
-    D.launches += 3;
-  } else {
-    ix->n_pos = n_positions;
-    ix->pos = dalloc<unsigned>(D, (size_t)n_positions + 1);
-    if (!ix->pos) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (position table)"); }
+  TableSlice S;
+  if (!build_slice(D, ix->ref, ix->k, 0ull, (unsigned long long)ix->n_buckets, S, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
+  ix->dir = S.dir; ix->heads = S.heads; ix->pos = S.pos; ix->n_pos = S.n_pos; ix->n_heads = S.n_occ;
+  {
+    const unsigned np = (unsigned)S.n_pos;
+    D.h2d(ix->heads + S.n_occ, &np, sizeof(unsigned));      // terminal entry
+    D.sync();
   }
   stamp(D, t1);
   D.sync();
@@ -487,8 +524,8 @@ int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec
 
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]) {
   if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
-  info[0] = ix->k; info[1] = ix->device; info[2] = ix->ref.n_words; info[3] = ix->n_buckets + 2; info[4] = ix->n_pos;
-  info[5] = (int64_t)ix->ref.n_words * 12 + (ix->n_buckets + 2) * 4 + (ix->n_pos + 1) * 4 + (ix->n_buckets / 32 + 2) * 4;
+  info[0] = ix->k; info[1] = ix->device; info[2] = ix->ref.n_words; info[3] = ix->n_heads; info[4] = ix->n_pos;
+  info[5] = (int64_t)ix->ref.n_words * 12 + (ix->n_buckets / 32 + 1) * 8 + (ix->n_heads + 2) * 4 + (ix->n_pos + 1) * 4;
   info[6] = ix->ref.n_seq; info[7] = ix->ref.n_bases;
   return MFSC_OK;
 }
@@ -497,9 +534,9 @@ int mfsc_index_buffers(const mfsc_index* ix, void* ptr[5], int64_t bytes[5]) {
   if (!ix) return fail(MFSC_ERR_ARG, "index is NULL");
   ptr[0] = ix->ref.txt; bytes[0] = (int64_t)ix->ref.n_words * 8;
   ptr[1] = ix->ref.inv; bytes[1] = (int64_t)ix->ref.n_words * 4;
-  ptr[2] = ix->H; bytes[2] = (ix->n_buckets + 2) * 4;
+  ptr[2] = ix->dir; bytes[2] = (ix->n_buckets / 32 + 1) * 8;
   ptr[3] = ix->pos; bytes[3] = (ix->n_pos + 1) * 4;
-  ptr[4] = ix->occ; bytes[4] = (ix->n_buckets / 32 + 2) * 4;
+  ptr[4] = ix->heads; bytes[4] = (ix->n_heads + 2) * 4;
   return MFSC_OK;
 }
 
@@ -630,12 +667,12 @@ int mfsc_comm_free(mfsc_comm* c) {
 
 #ifndef MFSC_EMU
 // an index of the root's shape on `device`, buffers from cudaMalloc, contents to be received
-static mfsc_index* index_shell(int device, int k, unsigned n_words, long long n_pos, const std::vector<unsigned>& h_start,
+static mfsc_index* index_shell(int device, int k, unsigned n_words, long long n_pos, long long n_heads, const std::vector<unsigned>& h_start,
                                const std::vector<int>& h_len, const std::vector<unsigned>& h_ostart, long long n_bases) {
   DeviceGuard g(device);
   mfsc_index* ix = new mfsc_index();
   ix->device = device; ix->plain = true;
-  ix->k = k; ix->n_buckets = 1ll << (2 * k); ix->n_pos = n_pos;
+  ix->k = k; ix->n_buckets = 1ll << (2 * k); ix->n_pos = n_pos; ix->n_heads = n_heads;
   ix->ref.n_seq = (int)h_len.size(); ix->ref.n_words = n_words; ix->ref.n_bases = n_bases;
   ix->ref.h_start = h_start; ix->ref.h_len = h_len; ix->h_ostart = h_ostart;
   const size_t ns = h_len.size();
@@ -644,9 +681,9 @@ static mfsc_index* index_shell(int device, int k, unsigned n_words, long long n_
             cudaMalloc(&ix->ref.start, sizeof(unsigned) * (ns + 1)) == cudaSuccess &&
             cudaMalloc(&ix->ref.len, sizeof(int) * (ns + 1)) == cudaSuccess &&
             cudaMalloc(&ix->ostart, sizeof(unsigned) * (ns + 1)) == cudaSuccess &&
-            cudaMalloc(&ix->H, sizeof(unsigned) * (size_t)(ix->n_buckets + 2)) == cudaSuccess &&
+            cudaMalloc(&ix->dir, sizeof(uint2) * (size_t)(ix->n_buckets / 32 + 1)) == cudaSuccess &&
             cudaMalloc(&ix->pos, sizeof(unsigned) * (size_t)(n_pos + 1)) == cudaSuccess &&
-            cudaMalloc(&ix->occ, sizeof(unsigned) * (size_t)(ix->n_buckets / 32 + 2)) == cudaSuccess;
+            cudaMalloc(&ix->heads, sizeof(unsigned) * (size_t)(n_heads + 2)) == cudaSuccess;
   if (ok) ok = cudaMemcpy(ix->ref.start, h_start.data(), sizeof(unsigned) * ns, cudaMemcpyHostToDevice) == cudaSuccess &&
                cudaMemcpy(ix->ref.len, h_len.data(), sizeof(int) * ns, cudaMemcpyHostToDevice) == cudaSuccess &&
                cudaMemcpy(ix->ostart, h_ostart.data(), sizeof(unsigned) * ns, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -670,8 +707,8 @@ int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms
     const size_t ns = (size_t)r->ref.n_seq;
     n->ref.txt = (unsigned long long*)dup(r->ref.txt, 8 * (size_t)r->ref.n_words); n->ref.inv = (unsigned*)dup(r->ref.inv, 4 * (size_t)r->ref.n_words);
     n->ref.start = (unsigned*)dup(r->ref.start, 4 * ns); n->ref.len = (int*)dup(r->ref.len, 4 * ns); n->ostart = (unsigned*)dup(r->ostart, 4 * ns);
-    n->H = (unsigned*)dup(r->H, 4 * (size_t)(r->n_buckets + 2)); n->pos = (unsigned*)dup(r->pos, 4 * (size_t)(r->n_pos + 1));
-    n->occ = (unsigned*)dup(r->occ, 4 * (size_t)(r->n_buckets / 32 + 2));
+    n->dir = (uint2*)dup(r->dir, 8 * (size_t)(r->n_buckets / 32 + 1)); n->pos = (unsigned*)dup(r->pos, 4 * (size_t)(r->n_pos + 1));
+    n->heads = (unsigned*)dup(r->heads, 4 * (size_t)(r->n_heads + 2));
     ix[i] = n;
   }
   return MFSC_OK;
@@ -699,7 +736,7 @@ int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms
     if (!r || r->device != c->devices[root]) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the root index does not live on devices[root]");
     for (int i = 0; i < c->world; i++) {
       if (i == root) continue;
-      ix[i] = index_shell(c->devices[i], r->k, r->ref.n_words, r->n_pos, r->ref.h_start, r->ref.h_len, r->h_ostart, r->ref.n_bases);
+      ix[i] = index_shell(c->devices[i], r->k, r->ref.n_words, r->n_pos, r->n_heads, r->ref.h_start, r->ref.h_len, r->h_ostart, r->ref.n_bases);
       if (!ix[i]) { for (int j = 0; j < i; j++) if (j != root) { mfsc_index_free(ix[j]); ix[j] = nullptr; } return fail(MFSC_ERR_NOMEM, "out of device memory (index replica)"); }
     }
     void* rp[5]; int64_t rb[5];
@@ -717,7 +754,7 @@ int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms
     mfsc_index* r = ix[0];
     if (c->rank == root) {
       if (!r) return fail(MFSC_ERR_ARG, "mfsc_index_broadcast: the root rank has no index");
-      meta[0] = r->k; meta[1] = r->ref.n_words; meta[2] = r->n_pos; meta[3] = r->ref.n_seq; meta[4] = r->ref.n_bases;
+      meta[0] = r->k; meta[1] = r->ref.n_words; meta[2] = r->n_pos; meta[3] = r->ref.n_seq; meta[4] = r->ref.n_bases; meta[5] = r->n_heads;
     }
     long long* d_meta = dalloc<long long>(D, 8);
     if (!d_meta) return fail(MFSC_ERR_NOMEM, "out of device memory (broadcast)");
@@ -746,7 +783,7 @@ int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms
       std::vector<unsigned> hs(tab.begin(), tab.begin() + ns), ho(tab.begin() + 2 * ns, tab.begin() + 3 * ns);
       std::vector<int> hl(ns);
       memcpy(hl.data(), tab.data() + ns, 4 * ns);
-      r = index_shell(D.device, (int)meta[0], (unsigned)meta[1], meta[2], hs, hl, ho, meta[4]);
+      r = index_shell(D.device, (int)meta[0], (unsigned)meta[1], meta[2], meta[5], hs, hl, ho, meta[4]);
       if (!r) return fail(MFSC_ERR_NOMEM, "out of device memory (index replica)");
       ix[0] = r;
     }
@@ -866,7 +903,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     if (rd->n_tiles > 0) {
       // persistent grid: warps take tiles of the query strands from a ticket counter
       MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, 8), MFSC_LANES * SEED_WARPS, 0, D.stream,
-                  RS, ix->ostart, ix->H, ix->pos, ix->occ, QS, ST, P, mo);
+                  RS, ix->ostart, ix->view(), QS, ST, P, mo);
       D.launches++;
     }
     D.d2h(&found, d_counter, sizeof(unsigned));

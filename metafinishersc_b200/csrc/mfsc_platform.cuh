@@ -36,6 +36,7 @@ extern thread_local emu_dim3 emu_threadIdx, emu_blockIdx, emu_blockDim, emu_grid
 #define gridDim emu_gridDim
 typedef int cudaStream_t;
 struct int4 { int x, y, z, w; };
+struct uint2 { unsigned x, y; };
 
 #define MFSC_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                        \

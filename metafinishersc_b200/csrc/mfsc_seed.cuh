@@ -44,9 +44,9 @@ MFSC_DEV unsigned mem_slot(unsigned* ctr) {
 // Stage 2 kernel.  A warp owns one tile of a query strand (SEED_TILE_WORDS packed words = 2048 bases):
 //   a. the tile's packed text and invalid mask are staged in shared memory with 128-bit / 64-bit coalesced loads
 //      (one load per lane), and every probe window is then cut out of shared memory;
-//   b. all lanes probe together, SEED_U probes per lane and round: k-mer -> one bit of the bucket occupancy bitmap
-//      (4^k / 8 bytes, resident in L2) -> only occupied buckets touch the bucket heads (the one table far larger
-//      than L2), SEED_U independent loads in flight per lane;
+//   b. all lanes probe together, SEED_U probes per lane and round: k-mer -> directory entry of its bucket word (occupancy
+//      bits + rank, 8 bytes per 32 buckets, resident in L2) -> only occupied buckets go on to the bucket heads,
+//      SEED_U independent loads in flight per lane;
 //   c. the probes that found candidates are compacted into a shared-memory list (ballot + popc) and dealt to the
 //      lanes one probe each, so the lanes verifying candidates are the ones that have any; buckets with more than
 //      SEED_HEAVY positions (repeats) are walked by the whole warp, 32 positions at a time;
@@ -89,7 +89,7 @@ MFSC_DEV unsigned sm_win32(const unsigned* inv, int pos) {
 }
 
 struct SeedCtx {
-  SeqStore R, Q; const unsigned* r_ostart; const unsigned* H; const unsigned* pos; DevParams P; MemOut out;
+  SeqStore R, Q; const unsigned* r_ostart; KmerIndex X; DevParams P; MemOut out;
   unsigned qstart; int qlen, qs;
 };
 
@@ -119,8 +119,10 @@ MFSC_DEV void seed_emit(const SeedCtx& C, unsigned r, int p, int left, int right
     const unsigned long long kmask = (1ull << (2 * k)) - 1ull;
     const unsigned long long km0 = win64(C.Q.txt, C.qstart + (unsigned)s2) & kmask;
     bool unique = true;
-    for (unsigned g = C.H[km0]; g < C.H[km0 + 1] && unique; g++) {
-      const unsigned r2 = C.pos[g];
+    unsigned g0 = 0, g1 = 0;
+    kmer_bucket(C.X, km0, g0, g1);
+    for (unsigned g = g0; g < g1 && unique; g++) {
+      const unsigned r2 = C.X.pos[g];
       if (r2 == s1p) continue;
       if (match_right(C.R, r2 + k, C.Q, C.qstart + (unsigned)s2 + k, total - k) >= total - k) unique = false;
     }
@@ -165,9 +167,8 @@ MFSC_DEV int seed_finish_long(const SeedCtx& C, unsigned r, int p, int right, in
 }
 
 // R: reference store; r_ostart[rec] = position of record rec's first base in the separator-joined
-// coordinate system the clustering stage works in (off[rec] + rec).  occ: one bit per bucket, set when it is not empty.
-MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, const unsigned* pos, const unsigned* occ, SeqStore Q,
-                    SeedTiles T, DevParams P, MemOut out) {
+// coordinate system the clustering stage works in (off[rec] + rec).  X: the k-mer index (mfsc_seq.cuh).
+MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore Q, SeedTiles T, DevParams P, MemOut out) {
 #ifdef MFSC_EMU
   static thread_local SeedShared sm_all[1];
   SeedShared& S = sm_all[0];
@@ -180,7 +181,8 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, con
   const unsigned long long kmask = (1ull << (2 * k)) - 1ull;
   const unsigned vmask = (1u << k) - 1u;
   const unsigned lt_mask = MFSC_LANES == 32 ? ((1u << lane) - 1u) : 0u;
-  SeedCtx C; C.R = R; C.Q = Q; C.r_ostart = r_ostart; C.H = H; C.pos = pos; C.P = P; C.out = out;
+  SeedCtx C; C.R = R; C.Q = Q; C.r_ostart = r_ostart; C.X = X; C.P = P; C.out = out;
+  const unsigned* pos = X.pos;
   const unsigned TICKET = 4;                     // consecutive tiles per ticket: the strand is looked up once per ticket
   for (;;) {
     unsigned t0 = 0;
@@ -235,16 +237,19 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, con
             km[u] = sm_win64(S.txt, lp) & kmask;
           }
         }
-        unsigned ow[SEED_U];
+        // directory entries first (SEED_U independent loads in flight), then the heads of the occupied buckets
+        uint2 dw[SEED_U];
 #pragma unroll
-        for (int u = 0; u < SEED_U; u++) ow[u] = live[u] ? ldg(&occ[km[u] >> 5]) : 0u;
+        for (int u = 0; u < SEED_U; u++) { dw[u].x = 0; dw[u].y = 0; if (live[u]) dw[u] = ldg(&X.dir[km[u] >> 5]); }
 #pragma unroll
         for (int u = 0; u < SEED_U; u++) {
-          live[u] = ((ow[u] >> (unsigned)(km[u] & 31ull)) & 1u) != 0u;
+          const unsigned bit = (unsigned)(km[u] & 31ull);
+          live[u] = ((dw[u].x >> bit) & 1u) != 0u;
           b0[u] = 0; b1[u] = 0;
-          // the bucket heads (1/4 GB and up) are touched once per occupied probe at random: stream them through L2 so
-          // that the bitmap, the position table and the packed reference text, which are reused, stay resident
-          if (live[u]) { b0[u] = ld_stream(&H[km[u]]); b1[u] = ld_stream(&H[km[u] + 1]); }
+          if (live[u]) {
+            const unsigned r = dw[u].y + (unsigned)dev_popc32(dw[u].x & ((1u << bit) - 1u));
+            b0[u] = ldg(&X.heads[r]); b1[u] = ldg(&X.heads[r + 1]);
+          }
         }
         // c. probes with candidates -> shared list (light buckets first, heavy ones from the top)
         int n_light = 0, n_heavy = 0;
@@ -324,23 +329,6 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, const unsigned* H, con
         wsync();
       }
     }
-  }
-}
-
-// occupancy bitmap of the bucket table: bit b of word w is set when bucket 32 w + b holds at least one position
-MFSC_KERNEL k_index_occ(const unsigned* H, long long n_buckets, unsigned* occ) {
-  const long long n_words = (n_buckets + 31) / 32;
-  for (long long w = thread_global(); w < n_words; w += threads_total()) {
-    unsigned bits = 0;
-    unsigned prev = H[w * 32];
-    for (int b = 0; b < 32; b++) {
-      const long long x = w * 32 + b;
-      if (x >= n_buckets) break;
-      const unsigned nx = H[x + 1];
-      if (nx > prev) bits |= 1u << b;
-      prev = nx;
-    }
-    occ[w] = bits;
   }
 }
 

@@ -135,10 +135,39 @@ MFSC_KERNEL k_pack(const unsigned char* bases, const long long* in_off, const un
 
 // ------------------------------------------------------------------------------------------
 // k-mer bucket index of the reference text (stage 1).
-//   H[0..4^k+1] : bucket b = pos[H[b] .. H[b+1])   (after k_index_fill)
-// Built as count -> inclusive scan -> fill.  One thread per text word (32 start positions).
+//
+// What the seed kernel reads (KmerIndex): most of the 4^k buckets are empty (k is chosen so that 4^k >= 4 R), so the
+// index keeps a DIRECTORY of one 8-byte entry per 32 buckets -- {occupancy bits, number of occupied buckets before this
+// word} -- and a bucket-start offset (`heads`) for the OCCUPIED buckets only:
+//     bucket b occupied  <=>  bit (b & 31) of dir[b >> 5].x
+//     its positions      =    pos[heads[r] .. heads[r + 1]),  r = dir[b >> 5].y + popc(dir[b >> 5].x & ((1 << (b & 31)) - 1))
+// For a 5-10 Mbp reference at k = 13 that is 16 MB of directory + 4 B per occupied bucket instead of 268 MB of dense
+// bucket heads: directory, heads, positions and text together fit the 126 MB L2, and four times less has to cross
+// NVLink when the index is replicated.
+//
+// Built from a dense histogram that is scratch: count -> inclusive scan -> fill -> directory bits -> scan of the
+// per-word counts -> heads.  One thread per text word (32 start positions).  The kernels take a bucket range
+// [b_lo, b_hi): a build can be restricted to a slice of the k-mer space (mfsc_index_build_sharded: every GPU of a
+// box builds one slice, the slices are exchanged with NCCL all-gathers).
 // ------------------------------------------------------------------------------------------
-MFSC_KERNEL k_index_count(const unsigned long long* txt, const unsigned* inv, unsigned n_words, int k, unsigned* H) {
+struct KmerIndex {
+  const uint2* dir;         // [4^k / 32 (+1)]
+  const unsigned* heads;    // [occupied buckets + 1]
+  const unsigned* pos;      // [indexed positions]
+};
+
+// bucket of k-mer km: false when it is empty
+MFSC_DEV bool kmer_bucket(const KmerIndex& X, unsigned long long km, unsigned& b0, unsigned& b1) {
+  const uint2 w = X.dir[km >> 5];
+  const unsigned bit = (unsigned)(km & 31ull);
+  if (!((w.x >> bit) & 1u)) return false;
+  const unsigned r = w.y + (unsigned)dev_popc32(w.x & ((1u << bit) - 1u));
+  b0 = X.heads[r]; b1 = X.heads[r + 1];
+  return true;
+}
+
+MFSC_KERNEL k_index_count(const unsigned long long* txt, const unsigned* inv, unsigned n_words, int k, unsigned long long b_lo,
+                          unsigned long long b_hi, unsigned* H) {
   const unsigned long long kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
   const unsigned vmask = (k >= 32) ? ~0u : ((1u << k) - 1u);
   for (long long w = thread_global(); w + 1 < (long long)n_words; w += threads_total()) {
@@ -150,13 +179,17 @@ MFSC_KERNEL k_index_count(const unsigned long long* txt, const unsigned* inv, un
       unsigned iw = b ? ((i0 >> b) | (i1 << (32 - b))) : i0;
       if (iw & vmask) continue;
       unsigned long long tw = b ? ((t0 >> (2 * b)) | (t1 << (64 - 2 * b))) : t0;
-      atomic_add_u32(&H[(tw & kmask) + 2], 1u);
+      const unsigned long long km = tw & kmask;
+      if (km < b_lo || km >= b_hi) continue;
+      atomic_add_u32(&H[(km - b_lo) + 2], 1u);
     }
   }
 }
 
-MFSC_KERNEL k_index_fill(const unsigned long long* txt, const unsigned* inv, unsigned n_words, int k, unsigned* H,
-                         unsigned* pos) {
+// after the inclusive scan H[x + 1] = first slot of bucket b_lo + x; the fill advances it to the bucket's end, so that
+// afterwards H[x] = first slot of bucket b_lo + x (and H[n] = total)
+MFSC_KERNEL k_index_fill(const unsigned long long* txt, const unsigned* inv, unsigned n_words, int k, unsigned long long b_lo,
+                         unsigned long long b_hi, unsigned* H, unsigned* pos) {
   const unsigned long long kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
   const unsigned vmask = (k >= 32) ? ~0u : ((1u << k) - 1u);
   for (long long w = thread_global(); w + 1 < (long long)n_words; w += threads_total()) {
@@ -168,8 +201,54 @@ MFSC_KERNEL k_index_fill(const unsigned long long* txt, const unsigned* inv, uns
       unsigned iw = b ? ((i0 >> b) | (i1 << (32 - b))) : i0;
       if (iw & vmask) continue;
       unsigned long long tw = b ? ((t0 >> (2 * b)) | (t1 << (64 - 2 * b))) : t0;
-      unsigned slot = atomic_add_u32(&H[(tw & kmask) + 1], 1u);
+      const unsigned long long km = tw & kmask;
+      if (km < b_lo || km >= b_hi) continue;
+      unsigned slot = atomic_add_u32(&H[(km - b_lo) + 1], 1u);
       pos[slot] = (unsigned)(w * 32 + b);
     }
   }
+}
+
+// directory bits of the words of a bucket slice (n_buckets a multiple of 32), and the number of occupied buckets per word
+MFSC_KERNEL k_index_dir_bits(const unsigned* H, long long n_buckets, unsigned* bits, unsigned* cnt) {
+  const long long n_words = n_buckets / 32;
+  for (long long w = thread_global(); w < n_words; w += threads_total()) {
+    unsigned m = 0;
+    unsigned prev = H[w * 32];
+    for (int b = 0; b < 32; b++) {
+      const unsigned nx = H[w * 32 + b + 1];
+      if (nx > prev) m |= 1u << b;
+      prev = nx;
+    }
+    bits[w] = m;
+    cnt[w] = (unsigned)dev_popc32(m);
+  }
+}
+
+// rank[w] = exclusive scan of cnt (done by the caller).  Writes dir[w] = {bits, rank_base + rank[w]} and the start offset
+// (pos_base + H[b]) of every occupied bucket into heads[rank[w] ...].
+MFSC_KERNEL k_index_heads(const unsigned* H, long long n_buckets, const unsigned* bits, const unsigned* rank, unsigned rank_base,
+                          unsigned pos_base, uint2* dir, unsigned* heads) {
+  const long long n_words = n_buckets / 32;
+  for (long long w = thread_global(); w < n_words; w += threads_total()) {
+    unsigned m = bits[w];
+    unsigned r = rank[w];
+    uint2 e; e.x = m; e.y = rank_base + r;
+    dir[w] = e;
+    while (m) {
+      const int b = dev_ffs32(m) - 1;
+      m &= m - 1u;
+      heads[r++] = pos_base + H[w * 32 + b];
+    }
+  }
+}
+
+// adds a constant to a range of directory ranks / heads (slices of a sharded build become global)
+MFSC_KERNEL k_add_u32(unsigned* a, long long n, unsigned v) {
+  for (long long i = thread_global(); i < n; i += threads_total()) a[i] += v;
+}
+
+// rank[w] = incl[w] - popc(bits[w]): the exclusive scan from the inclusive one
+MFSC_KERNEL k_excl_from_incl(const unsigned* incl, const unsigned* bits, long long n, unsigned* rank) {
+  for (long long i = thread_global(); i < n; i += threads_total()) rank[i] = incl[i] - (unsigned)dev_popc32(bits[i]);
 }

@@ -40,11 +40,11 @@ class Index:
     def info(self):
         a = np.zeros(8, dtype=np.int64)
         check(self.L, self.L.mfsc_index_info(self.h, ptr(a)))
-        return dict(k=int(a[0]), device=int(a[1]), text_words=int(a[2]), buckets=int(a[3]), positions=int(a[4]), hbm_bytes=int(a[5]),
+        return dict(k=int(a[0]), device=int(a[1]), text_words=int(a[2]), occupied_buckets=int(a[3]), positions=int(a[4]), hbm_bytes=int(a[5]),
                     records=int(a[6]), bases=int(a[7]))
 
     def buffers(self):
-        """[(device pointer, bytes)] x 5: packed text, invalid mask, bucket heads, positions, occupancy bitmap."""
+        """[(device pointer, bytes)] x 5: packed text, invalid mask, bucket directory, positions, heads of the occupied buckets."""
         p = (ctypes.c_void_p * 5)()
         b = np.zeros(5, dtype=np.int64)
         check(self.L, self.L.mfsc_index_buffers(self.h, p, ptr(b)))
