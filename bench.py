@@ -47,7 +47,7 @@ OPS_PER_CELL = 12      # SASS of the packed cell (k_extend<false,true>): 1 VIMNM
 WORKLOADS = {
     "cfg1": "cfg1: README shape, 2 x 5 Mbp chimeric contigs, 58332 reads x 6 kbp, 1% del + 1% ins, per GPU",
     "cfg2": "cfg2: 5 Mbp genome, 50X, 10 kbp reads, 15% indel (p_del=p_ins=0.075), 25000 reads/GPU",
-    "cfg3": "cfg3: 10 genomes x 5 Mbp (10 chimeric contigs), log-normal 5-200X, %d reads x 10 kbp, 1% del + 1% ins, per GPU",
+    "cfg3": "cfg3: 10 genomes x 5 Mbp (10 chimeric contigs), log-normal 5-200X, %d reads x 10 kbp, 1%% del + 1%% ins, per GPU",
     "cfg4": "cfg4: first %d reads (10 kbp, 1%% error) of the cfg5 read set, doubled by writeToFile_Double1 (Read_p + Read_d), aligned against themselves, per GPU",
     "cfg5": "cfg5: 100 genomes x 5 Mbp (500 Mbp of contigs), uniform 30X; a %d-read sample (x 10 kbp, 1%% error) of the 1.5 M reads per step, per GPU",
 }
@@ -278,13 +278,20 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
         th = threading.Thread(target=up)
         th.start()                                  # the rank's read batch goes up (and is packed) while the index is made
         ix = None
-        if rank == 0:
-            ix = E.index((hcb, hco), P)
+        if world > 1 and args.strong_index == "sharded":
+            # every rank builds 1/N of the k-mer space, the slices are exchanged over NVLink (mfsc_index_build_sharded)
+            ix, bms = comm.build_sharded((hcb, hco), P)
+            parts["index_sharded_upload_ms"], parts["index_sharded_slice_ms"], parts["index_sharded_exchange_ms"] = bms[0], bms[1], bms[2]
             parts["index_build_ms"] = (time.perf_counter() - t0) * 1e3
-        tb = time.perf_counter()
-        if world > 1:
-            ix, _ = comm.broadcast(ix, len(hco) - 1, root=0)
-        parts["broadcast_ms"] = (time.perf_counter() - tb) * 1e3 if world > 1 else 0.0
+            parts["broadcast_ms"] = 0.0
+        else:
+            if rank == 0:
+                ix = E.index((hcb, hco), P)
+                parts["index_build_ms"] = (time.perf_counter() - t0) * 1e3
+            tb = time.perf_counter()
+            if world > 1:
+                ix, _ = comm.broadcast(ix, len(hco) - 1, root=0)
+            parts["broadcast_ms"] = (time.perf_counter() - tb) * 1e3 if world > 1 else 0.0
         th.join()
         if "err" in box:
             raise box["err"]
@@ -332,8 +339,10 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
     return {"workload": "cfg3 as one job: 10 chimeric contigs x %d bp, %d reads x 10 kbp (%.0f Mbp), 1%% del + 1%% ins, contiguous read "
                         "batches over %d rank(s)" % (G, n_total, bases_total / 1e6, world),
             "scaling": "strong", "value": bases_total * K / (wall_max * 1e-3) / 1e6, "unit": "Mbp/s", "steps": K, "ms_per_step": wall_max / K,
-            "inside_the_wall": "index build (rank 0, from pinned host contigs) + NCCL broadcast of the 5 index buffers + H2D and packing of "
-                               "the rank's reads (second host thread/stream, overlapped with build+broadcast) + stages 2-4 + rows to the "
+            "index": ("sharded build: every rank packs the contigs and builds 1/N of the k-mer space, slices exchanged with grouped NCCL broadcasts"
+                      if world > 1 and args.strong_index == "sharded" else "built on rank 0, NCCL broadcast of the 5 index buffers") if world > 1 else "built in place",
+            "inside_the_wall": "index (see `index`; from pinned host contigs) + H2D and packing of "
+                               "the rank's reads (second host thread/stream, overlapped with the index build) + stages 2-4 + rows to the "
                                "host + rows gathered on rank 0 in rank order; host clock, barrier both sides, max over ranks",
             "rank0_breakdown_ms": {k: v for k, v in last.items() if k.endswith("_ms")}, "rank0_stage_ms": last["stage_ms"],
             "align_ms_max_over_ranks": align_max, "align_ms_min_over_ranks": align_min, "rows_total": last["rows_total"]}
@@ -398,6 +407,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the sharded cfg3 job")
     ap.add_argument("--no-wrapper", action="store_true", help="skip the file-level alignerRobot.largeRvsQAlign measurement")
     ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--strong-index", default="sharded", choices=["sharded", "broadcast"],
+                    help="N > 1: every rank builds 1/N of the index and the slices are exchanged (sharded), or rank 0 builds and broadcasts")
     ap.add_argument("--strong-genome", type=int, default=5_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -99,6 +99,12 @@ int mfsc_comm_init_rank(const uint8_t id[128], int32_t rank, int32_t world, mfsc
 int mfsc_comm_init_local(const int32_t* devices, int32_t n, mfsc_comm** out);
 int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms);
 int mfsc_comm_free(mfsc_comm* c);
+/* Sharded build, one process per GPU: every rank calls it with the same contigs; rank r builds the tables of its 1/N of the
+ * k-mer space and the slices are exchanged with grouped NCCL broadcasts (one root per slice).  Every rank ends with the
+ * complete index.  ms (optional): [0] upload + packing, [1] own slice, [2] exchange, [3] total (host clock).  With a
+ * communicator of one rank this is mfsc_index_build. */
+int mfsc_index_build_sharded(mfsc_comm* c, const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
+                             mfsc_index** out, double ms[4]);
 
 /* read batch upload (host -> HBM, packs both strands) */
 int mfsc_reads_upload(const uint8_t* bases, const int64_t* read_off, int32_t n_reads, mfsc_reads** out);

@@ -42,7 +42,7 @@ KEEP_MEMS, KEEP_CLUSTERS, STOP_SEEDS, STOP_CLUSTERS, WANT_DELTAS = 1, 2, 4, 8, 1
 SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_device", "mfsc_thread_release", "mfsc_default_params",
            "mfsc_host_alloc", "mfsc_host_free", "mfsc_index_build", "mfsc_index_create", "mfsc_index_info",
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_comm_unique_id", "mfsc_comm_init_rank",
-           "mfsc_comm_init_local", "mfsc_index_broadcast", "mfsc_comm_free", "mfsc_reads_upload", "mfsc_reads_free",
+           "mfsc_comm_init_local", "mfsc_index_broadcast", "mfsc_comm_free", "mfsc_index_build_sharded", "mfsc_reads_upload", "mfsc_reads_free",
            "mfsc_align_reads", "mfsc_align_batch", "mfsc_result_count", "mfsc_result_rows", "mfsc_result_mems",
            "mfsc_result_clusters", "mfsc_result_deltas", "mfsc_result_stats", "mfsc_result_free", "mfsc_coverage", "mfsc_cov_build", "mfsc_cov_fetch", "mfsc_cov_interval_sums", "mfsc_cov_free", "mfsc_row_flags", "mfsc_write_coords",
            "mfsc_write_delta", "mfsc_fasta_parse", "mfsc_fasta_count", "mfsc_fasta_write"]
@@ -75,6 +75,7 @@ def bind(path):
     L.mfsc_comm_init_local.argtypes = [c_vp, c_i32, ctypes.POINTER(c_vp)]
     L.mfsc_index_broadcast.argtypes = [c_vp, c_i32, c_vp, ctypes.POINTER(c_dbl)]
     L.mfsc_comm_free.argtypes = [c_vp]
+    L.mfsc_index_build_sharded.argtypes = [c_vp, c_vp, c_vp, c_i32, PP, ctypes.POINTER(c_vp), c_vp]
     L.mfsc_reads_upload.argtypes = [c_vp, c_vp, c_i32, ctypes.POINTER(c_vp)]
     L.mfsc_reads_free.argtypes = [c_vp]
     L.mfsc_align_reads.argtypes = [c_vp, c_vp, PP, c_i32, ctypes.POINTER(c_vp)]

@@ -77,7 +77,20 @@ def clear_caches():
         _ROWS_CACHE.clear()
 
 
+_BATCH_SIGS = None     # inside one batch call: path -> signature (a reference shared by 20 jobs is hashed once)
+
+
 def _content_signature(path):
+    memo = _BATCH_SIGS
+    if memo is not None:
+        key = os.path.abspath(path)
+        if key not in memo:
+            memo[key] = _content_signature_now(path)
+        return memo[key]
+    return _content_signature_now(path)
+
+
+def _content_signature_now(path):
     """Identifies the CONTENT of a reference file, not its path or time stamp: IORobot.alignWithName rewrites
     `<name>leftSeg.fasta` in place on every call, usually with the same size, and a coarse mtime (1 s, NFS) would
     make (path, mtime, size) collide.  Files up to 64 MB are hashed whole (a few ms); larger ones by size, inode,
@@ -305,6 +318,180 @@ def _align_job(folderName, outputName, referenceName, queryName, specialForRaw, 
     return rs
 
 
+_SUPER_BASES = 64_000_000      # query bases per GPU call when jobs are merged (a 10 kb noisy read keeps one warp busy for
+                               # milliseconds, so a 12.5 Mbp part alone fills a quarter of the resident warps)
+
+
+def _merge_queries(entries):
+    """entries: [(names, bases, off), ...] -> (bases, off) of their concatenation; adjacent views into one parent array are
+    merged without a copy (the parts handed over by the splitter are)."""
+    if len(entries) == 1:
+        return entries[0][1], entries[0][2]
+    bufs = [e[1] for e in entries]
+    adjacent = all(isinstance(b, np.ndarray) and b.base is not None and b.base is bufs[0].base for b in bufs)
+    if adjacent:
+        addr = [b.__array_interface__["data"][0] for b in bufs]
+        adjacent = all(addr[i] + bufs[i].size == addr[i + 1] for i in range(len(bufs) - 1))
+    total = sum(int(b.size) for b in bufs)
+    if adjacent:
+        parent = bufs[0].base
+        start = addr[0] - parent.__array_interface__["data"][0]
+        merged = parent[start:start + total] if parent.dtype == np.uint8 and parent.ndim == 1 else np.concatenate(bufs)
+    else:
+        merged = np.concatenate(bufs)
+    offs, acc = [np.zeros(1, dtype=np.int64)], 0
+    for e in entries:
+        o = np.asarray(e[2], dtype=np.int64)
+        offs.append(o[1:] - o[0] + acc)
+        acc += int(o[-1] - o[0])
+    return merged, np.concatenate(offs)
+
+
+def _split_rows(rows, bounds):
+    """Rows of a merged batch (ascending read index) -> one Rows per [b, e) read range, read ids rebased."""
+    cut = np.searchsorted(rows.qry_id, [b for b, _ in bounds] + [bounds[-1][1]]) if len(rows) else np.zeros(len(bounds) + 1, dtype=np.int64)
+    out = []
+    for k, (b, e) in enumerate(bounds):
+        lo, hi = int(cut[k]), int(cut[k + 1])
+        r = _engine_mod.Rows()
+        for f in ("ref_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            setattr(r, f, np.ascontiguousarray(getattr(rows, f)[lo:hi]))
+        r.qry_id = np.ascontiguousarray(rows.qry_id[lo:hi] - b)
+        r.stats, r.ms, r.mems, r.clusters = rows.stats, rows.ms, None, None
+        r.delta_begin = r.delta_end = r.deltas = None
+        if rows.deltas is not None and hi > lo:
+            db, de = rows.delta_begin[lo:hi], rows.delta_end[lo:hi]
+            ok = db >= 0
+            d0 = int(db[ok].min()) if ok.any() else 0
+            d1 = int(de[ok].max()) if ok.any() else 0
+            r.deltas = np.ascontiguousarray(rows.deltas[d0:d1])
+            r.delta_begin = np.where(ok, db - d0, -1).astype(np.int64)
+            r.delta_end = np.where(ok, de - d0, -1).astype(np.int64)
+        elif rows.deltas is not None:
+            r.deltas = np.zeros(0, dtype=np.int32)
+            r.delta_begin = np.zeros(0, dtype=np.int64)
+            r.delta_end = np.zeros(0, dtype=np.int64)
+        out.append(r)
+    return out
+
+
+def _batch_serial(folderName, workerList, specialForRaw, refinedVersion):
+    """The jobs of one batch call on one GPU.  Consecutive jobs that share the reference are merged into GPU calls of about
+    _SUPER_BASES query bases (every read is aligned on its own, so the rows of a merged call split exactly into the rows of
+    its jobs); the next merged batch is uploaded and packed by a second host thread while the current one is aligned, and
+    the .delta / coords text of the finished jobs is written on the writer pool."""
+    import queue
+    E = get_engine()
+    params = _params(refinedVersion)
+    flags = _engine_mod.WANT_DELTAS if fullDelta else 0
+    jobs = []
+    for outputName, referenceName, queryName, specialName in workerList:
+        qry = queryName if specialForRaw else folderName + queryName
+        jobs.append(dict(prefix=folderName + outputName, ref=folderName + referenceName, qry=qry,
+                         out=folderName + (specialName if specialForRaw else outputName + "Out")))
+    k = 0
+    while k < len(jobs):
+        g = k
+        while g < len(jobs) and jobs[g]["ref"] == jobs[k]["ref"]:
+            g += 1
+        group, k = jobs[k:g], g
+        ref_path = group[0]["ref"]
+        live = []
+        for j in group:
+            with _CACHE_LOCK:
+                parsed = _QUERY_CACHE.get(os.path.abspath(j["qry"]))
+            if not (os.path.exists(ref_path) and (parsed is not None or os.path.exists(j["qry"]))):
+                print("ERROR: Could not find input file(s) %s %s" % (ref_path, j["qry"]))   # nucmer's failure is ignored upstream too
+                delta = j["prefix"] + ".delta"
+                with _CACHE_LOCK:
+                    _ROWS_CACHE.pop(delta, None)
+                _PENDING_ROWS.pop(delta, None)
+                if os.path.exists(delta):
+                    os.remove(delta)
+                open(j["out"], "w").close()
+                continue
+            j["parsed"] = parsed
+            live.append(j)
+        if not live:
+            continue
+        ix, rnames, rlens = _get_index(E, ref_path, params)
+        dev = ix.info()["device"]
+        # merged batches
+        batches, cur, cur_bases = [], [], 0
+        for j in live:
+            if j["parsed"] is None:
+                j["parsed"] = fasta.read_fasta_arrays(j["qry"])
+            nb = int(j["parsed"][2][-1] - j["parsed"][2][0])
+            if cur and cur_bases + nb > _SUPER_BASES:
+                batches.append(cur)
+                cur, cur_bases = [], 0
+            cur.append(j)
+            cur_bases += nb
+        if cur:
+            batches.append(cur)
+        q = queue.Queue(maxsize=2)
+
+        def uploader():
+            E2 = None
+            try:
+                E2 = _engine_mod.Engine(E.L)
+                E2.set_device(dev)
+                for b in batches:
+                    buf, off = _merge_queries([j["parsed"] for j in b])
+                    q.put((b, E2.upload((buf, off)) if len(off) > 1 else None, None))
+            except Exception as e:        # surfaced in the caller's thread
+                q.put((None, None, e))
+            finally:
+                if E2 is not None:
+                    E2.thread_release()
+        th = threading.Thread(target=uploader)
+        th.start()
+        try:
+            for _ in batches:
+                b, reads, err = q.get()
+                if err is not None:
+                    raise err
+                if reads is None:
+                    rows = E.align(ix, [], params)
+                else:
+                    try:
+                        rows = E.align_reads(ix, reads, params, flags)
+                    except _engine_mod._lib.MfscError as e:
+                        if not fullDelta or "delta lists" not in str(e):
+                            raise
+                        print("note: delta lists did not fit, writing alignment headers only (%s)" % e)
+                        rows = E.align_reads(ix, reads, params, 0)
+                    finally:
+                        reads.free()
+                bounds, acc = [], 0
+                for j in b:
+                    n = len(j["parsed"][2]) - 1
+                    bounds.append((acc, acc + n))
+                    acc += n
+                for j, r in zip(b, _split_rows(rows, bounds)):
+                    qnames = [n.split()[0] if n.split() else n for n in j["parsed"][0]]
+                    qlens = np.diff(j["parsed"][2]).tolist()
+                    rs = RowSet(r, rnames, rlens, qnames, qlens, ref_path, j["qry"])
+                    _finish_job(E, j["prefix"], j["out"], rs)
+        finally:
+            th.join()
+    _join_writes()
+
+
+def _finish_job(E, prefix, out, rs):
+    """The files of one finished job, on the writer pool: <prefix>.delta, then the coords table."""
+    delta = prefix + ".delta"
+    with _CACHE_LOCK:
+        _ROWS_CACHE.pop(delta, None)
+    _PENDING_ROWS[delta] = rs
+
+    def write():
+        E.write_delta(delta, rs.rows, rs.ref_names, rs.ref_lens, rs.qry_names, rs.qry_lens, os.path.abspath(rs.ref_path), os.path.abspath(rs.qry_path))
+        _rows_cache_put(delta, rs)
+        E.write_coords(out, rs.rows, rs.ref_names, rs.qry_names, rs.ref_path, rs.qry_path, True)
+    _submit(write)
+
+
 def useMummerAlign(mummerLink, folderName, outputName, referenceName, queryName, specialForRaw=False, specialName="",
                    refinedVersion=False):
     _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
@@ -337,9 +524,12 @@ def useMummerAlignBatch(mummerLink, folderName, workerList, nProc, specialForRaw
         if houseKeeper.globalGPUs > 1 and len(workerList) > 1:
             _batch_on_gpus(folderName, workerList, specialForRaw, refinedVersion, houseKeeper.globalGPUs)
             return
-        for outputName, referenceName, queryName, specialName in workerList:
-            _align_job(folderName, outputName, referenceName, queryName, specialForRaw, specialName, refinedVersion)
-        _join_writes()
+        global _BATCH_SIGS
+        _BATCH_SIGS = {}
+        try:
+            _batch_serial(folderName, workerList, specialForRaw, refinedVersion)
+        finally:
+            _BATCH_SIGS = None
         return
     # globalLarge (alignerRobot.py:168-236): reference and query are each split into 10 parts (written to the CWD, where
     # fasta-splitter.pl puts them), every (reference part i, query part j) tile is its own nucmer job

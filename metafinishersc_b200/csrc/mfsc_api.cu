@@ -803,6 +803,104 @@ int mfsc_index_broadcast(mfsc_comm* c, int32_t root, mfsc_index** ix, double* ms
 #endif
 }
 
+// Sharded build (one process per GPU): every rank packs the contigs, builds the tables of ITS slice of the k-mer space
+// (count / fill touch only k-mers of the slice, the dense scratch histogram is 4^k / N entries), and the slices are
+// exchanged with grouped NCCL broadcasts, one root per slice (an all-gather of unequal pieces) -- the build time divides by
+// N and what crosses NVLink is the compact index once.
+int mfsc_index_build_sharded(mfsc_comm* c, const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p, mfsc_index** out,
+                             double ms[4]) {
+  if (!c || !bases || !rec_off || n_rec <= 0 || !out) return fail(MFSC_ERR_ARG, "mfsc_index_build_sharded: bad arguments");
+  if (ms) ms[0] = ms[1] = ms[2] = ms[3] = 0;
+  if (c->rank < 0 || c->world == 1) {
+    if (c->rank < 0 && c->world > 1) return fail(MFSC_ERR_ARG, "mfsc_index_build_sharded: needs a one-process-per-GPU communicator (mfsc_comm_init_rank)");
+    return mfsc_index_build(bases, rec_off, n_rec, p, out);
+  }
+#ifdef MFSC_EMU
+  return mfsc_index_build(bases, rec_off, n_rec, p, out);
+#else
+  int rc = check_params(p); if (rc) return rc;
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device (libmfsc_b200 has no CPU fallback)");
+  const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+  mfsc_index* ix = new mfsc_index();
+  ix->device = D.device;
+  std::string err;
+  if (!seq_upload(D, bases, rec_off, n_rec, 0, true, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
+  ix->h_ostart.resize(n_rec);
+  for (int r = 0; r < n_rec; r++) ix->h_ostart[r] = (unsigned)(rec_off[r] - rec_off[0] + r);
+  ix->ostart = dalloc<unsigned>(D, n_rec);
+  if (!ix->ostart) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (record table)"); }
+  D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
+  ix->k = choose_k(p, ix->ref.n_bases);
+  ix->n_buckets = 1ll << (2 * ix->k);
+  const int N = c->world, me = c->rank;
+  const long long words = ix->n_buckets / 32;
+  auto word_lo = [&](int r) { return words * r / N; };
+  if (ms) ms[0] = since(t0);
+  const auto t1 = std::chrono::steady_clock::now();
+  TableSlice S;
+  if (!build_slice(D, ix->ref, ix->k, (unsigned long long)word_lo(me) * 32ull, (unsigned long long)word_lo(me + 1) * 32ull, S, err)) {
+    index_release(D, ix); return fail(MFSC_ERR_NOMEM, err);
+  }
+  if (ms) ms[1] = since(t1);
+  const auto t2 = std::chrono::steady_clock::now();
+  // sizes of all slices
+  std::vector<long long> sizes(2 * N, 0);
+  sizes[2 * me] = S.n_occ; sizes[2 * me + 1] = S.n_pos;
+  long long* d_sizes = dalloc<long long>(D, 2 * N);
+  if (!d_sizes) { slice_free(D, S); index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (sizes)"); }
+  D.h2d(d_sizes, sizes.data(), sizeof(long long) * 2 * N);
+  int nrc = g_nccl.GroupStart();
+  for (int r = 0; r < N && !nrc; r++) nrc = g_nccl.Broadcast(d_sizes + 2 * r, d_sizes + 2 * r, 16, NCCL_U8, r, c->comms[0], c->streams[0]);
+  { int e2 = g_nccl.GroupEnd(); if (!nrc) nrc = e2; }
+  if (nrc) { D.free_(d_sizes); slice_free(D, S); index_release(D, ix); return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(nrc)); }
+  D.d2h(sizes.data(), d_sizes, sizeof(long long) * 2 * N);
+  D.free_(d_sizes);
+  std::vector<long long> occ_off(N + 1, 0), pos_off(N + 1, 0);
+  for (int r = 0; r < N; r++) { occ_off[r + 1] = occ_off[r] + sizes[2 * r]; pos_off[r + 1] = pos_off[r] + sizes[2 * r + 1]; }
+  ix->n_heads = occ_off[N]; ix->n_pos = pos_off[N];
+  if ((unsigned long long)ix->n_pos >= 0xffffffffull) { slice_free(D, S); index_release(D, ix); return fail(MFSC_ERR_ARG, "reference too large"); }
+  ix->dir = dalloc<uint2>(D, words + 1); ix->heads = dalloc<unsigned>(D, ix->n_heads + 2); ix->pos = dalloc<unsigned>(D, ix->n_pos + 1);
+  if (!ix->dir || !ix->heads || !ix->pos) { slice_free(D, S); index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (index)"); }
+  // own slice into place, ranks and position offsets made global
+  if (S.n_words) {
+    MFSC_LAUNCH(k_dir_place, grid_for(D, S.n_words, 256, 16), 256, 0, D.stream, S.dir, S.n_words, (unsigned)occ_off[me], ix->dir + word_lo(me));
+    D.launches++;
+  }
+  if (S.n_occ) {
+    MFSC_LAUNCH(k_copy_add_u32, grid_for(D, S.n_occ, 256, 16), 256, 0, D.stream, S.heads, (long long)S.n_occ, (unsigned)pos_off[me], ix->heads + occ_off[me]);
+    D.launches++;
+  }
+  if (S.n_pos) cudaMemcpyAsync(ix->pos + pos_off[me], S.pos, sizeof(unsigned) * (size_t)S.n_pos, cudaMemcpyDeviceToDevice, D.stream);
+  {
+    const unsigned np = (unsigned)ix->n_pos;
+    D.h2d(ix->heads + ix->n_heads, &np, sizeof(unsigned));
+  }
+  // exchange: slice r comes from rank r
+  for (int what = 0; what < 3 && !nrc; what++) {
+    nrc = g_nccl.GroupStart();
+    for (int r = 0; r < N && !nrc; r++) {
+      char* buf; size_t bytes;
+      if (what == 0) { buf = (char*)(ix->dir + word_lo(r)); bytes = sizeof(uint2) * (size_t)(word_lo(r + 1) - word_lo(r)); }
+      else if (what == 1) { buf = (char*)(ix->heads + occ_off[r]); bytes = sizeof(unsigned) * (size_t)sizes[2 * r]; }
+      else { buf = (char*)(ix->pos + pos_off[r]); bytes = sizeof(unsigned) * (size_t)sizes[2 * r + 1]; }
+      if (bytes) nrc = g_nccl.Broadcast(buf, buf, bytes, NCCL_U8, r, c->comms[0], c->streams[0]);
+    }
+    int e2 = g_nccl.GroupEnd(); if (!nrc) nrc = e2;
+  }
+  D.sync();
+  slice_free(D, S);
+  if (nrc) { index_release(D, ix); return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(nrc)); }
+  if (ms) { ms[2] = since(t2); ms[3] = since(t0); }
+  ix->build_ms = since(t0); ix->tables_ms = ms ? ms[1] : 0;
+  std::string msg;
+  if (!dev_check(msg)) { index_release(D, ix); return fail(MFSC_ERR_CUDA, "sharded index build: " + msg); }
+  *out = ix;
+  return MFSC_OK;
+#endif
+}
+
 static void reads_release(Dev& D, mfsc_reads* r) {
   if (!r) return;
   if (!D.stream || (r->device >= 0 && r->device != D.device)) {

@@ -252,3 +252,11 @@ MFSC_KERNEL k_add_u32(unsigned* a, long long n, unsigned v) {
 MFSC_KERNEL k_excl_from_incl(const unsigned* incl, const unsigned* bits, long long n, unsigned* rank) {
   for (long long i = thread_global(); i < n; i += threads_total()) rank[i] = incl[i] - (unsigned)dev_popc32(bits[i]);
 }
+
+// slice of a sharded build into the global arrays: directory words with their ranks made global, heads with their offsets made global
+MFSC_KERNEL k_dir_place(const uint2* src, long long n, unsigned rank_base, uint2* dst) {
+  for (long long i = thread_global(); i < n; i += threads_total()) { uint2 e = src[i]; e.y += rank_base; dst[i] = e; }
+}
+MFSC_KERNEL k_copy_add_u32(const unsigned* src, long long n, unsigned v, unsigned* dst) {
+  for (long long i = thread_global(); i < n; i += threads_total()) dst[i] = src[i] + v;
+}

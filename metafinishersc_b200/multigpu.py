@@ -66,6 +66,17 @@ class RankComm:
             index = Index(self.L, ctypes.c_void_p(arr[0]), n_rec)
         return index, ms.value
 
+    def build_sharded(self, contigs, params):
+        """Every rank calls it with the same contigs: rank r builds 1/N of the k-mer space, the slices are exchanged over
+        NVLink (mfsc_index_build_sharded).  Returns (Index, [upload, own slice, exchange, total] ms)."""
+        from .engine import _as_buf
+        buf, off = _as_buf(contigs)
+        h = ctypes.c_void_p()
+        ms = np.zeros(4, dtype=np.float64)
+        _lib.check(self.L, self.L.mfsc_index_build_sharded(self.h, _lib.ptr(buf), _lib.ptr(off), len(off) - 1, ctypes.byref(params),
+                                                           ctypes.byref(h), _lib.ptr(ms)))
+        return Index(self.L, h, len(off) - 1), ms.tolist()
+
     def free(self):
         if self.h:
             self.L.mfsc_comm_free(self.h)
