@@ -261,6 +261,13 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gbuf = {}
+    if world > 1:
+        cap = 2 * (n_total // world + 1)
+        gbuf = {"cap": cap, "cnt": torch.zeros(1, dtype=torch.int64, device="cuda"), "all": torch.zeros(world, dtype=torch.int64, device="cuda"),
+                "mine": torch.zeros((cap, 8), dtype=torch.int32, device="cuda"), "stage": torch.zeros((4 * cap, 8), dtype=torch.int32).pin_memory(),
+                "list": [torch.zeros((cap, 8), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None}
+
     def one_step():
         parts = {}
         box = {}
@@ -302,18 +309,22 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
         tg = time.perf_counter()
         n_rows = len(r)
         if world > 1:
-            # rows to rank 0 in rank order (= the global read order): counts first, then one padded gather
-            cnt = torch.tensor([n_rows], dtype=torch.int64, device="cuda")
-            allc = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(allc, cnt)
-            mx = int(max(int(c.item()) for c in allc))
-            mine = torch.zeros((mx, 8), dtype=torch.int32, device="cuda")
+            # rows to rank 0 in rank order (= the global read order): the counts with one all-gather, then one gather of
+            # fixed-size device buffers (capacity: 2 rows per read of the largest shard, grown when a step needs more)
+            cap = gbuf["cap"]
+            gbuf["cnt"][0] = n_rows
+            dist.all_gather_into_tensor(gbuf["all"], gbuf["cnt"])
+            counts_h = gbuf["all"].cpu().tolist()
+            if max(counts_h) > cap:
+                cap = gbuf["cap"] = 2 * max(counts_h)
+                gbuf["mine"] = torch.zeros((cap, 8), dtype=torch.int32, device="cuda")
+                gbuf["list"] = [torch.zeros_like(gbuf["mine"]) for _ in range(world)] if rank == 0 else None
             if n_rows:
-                mine[:n_rows] = torch.from_numpy(np.stack([r.ref_id, r.qry_id + a, r.s1, r.e1, r.s2, r.e2, r.errors, r.cols], axis=1)).cuda()
-            gl = [torch.zeros_like(mine) for _ in range(world)] if rank == 0 else None
-            dist.gather(mine, gl, dst=0)
+                gbuf["stage"][:n_rows] = torch.from_numpy(np.stack([r.ref_id, r.qry_id + a, r.s1, r.e1, r.s2, r.e2, r.errors, r.cols], axis=1))
+                gbuf["mine"][:n_rows].copy_(gbuf["stage"][:n_rows], non_blocking=True)
+            dist.gather(gbuf["mine"], gbuf["list"], dst=0)
             if rank == 0:
-                allrows = torch.cat([g[:int(c.item())] for g, c in zip(gl, allc)]).cpu().numpy()
+                allrows = torch.cat([g[:c] for g, c in zip(gbuf["list"], counts_h)]).cpu().numpy()
                 n_rows = len(allrows)
         parts["gather_ms"] = (time.perf_counter() - tg) * 1e3
         barrier()

@@ -191,9 +191,9 @@ int mfsc_row_flags(int64_t n_rows, const int32_t* ref_id, const int32_t* qry_id,
 /* show-coords -r text (5 header lines, rows "%8d %8d  | %8d %8d  | %8d %8d  | %8.2f  | %s\t%s") and the
  * delta file of a row set.  names: NUL-separated, one per record.  The delta carries the alignment
  * headers (`>ref qry lenR lenQ`, `sR eR sQ eQ errors simErrors 0`) followed by the indel offset list when the
- * batch was aligned with MFSC_WANT_DELTAS.  Without it (the default, traceback-free DP) the list is empty and
- * the 7th header field holds the alignment column count (MUMmer writes stop codons there, always 0 for nucmer)
- * so that %IDY stays reproducible from the file. */
+ * batch was aligned with MFSC_WANT_DELTAS.  Without it (the default, traceback-free DP) the file is NOT a MUMmer delta
+ * and says so in a `#MFSC rows-only` third line: every alignment is its header alone, with the alignment column count
+ * in the 7th field (MUMmer writes stop codons there, always 0 for nucmer) so that %IDY stays reproducible from the file. */
 int mfsc_write_coords(const char* path, const char* ref_path, const char* qry_path, int64_t n_rows,
                       const int32_t* ref_id, const int32_t* qry_id, const int32_t* s1, const int32_t* e1,
                       const int32_t* s2, const int32_t* e2, const int32_t* errors, const int32_t* cols,

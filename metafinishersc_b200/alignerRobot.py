@@ -52,7 +52,10 @@ def _join_writes():
                 return
             f = _PENDING.pop(0)
         f.result()
-fullDelta = True       # write real MUMmer delta records (indel offset lists); False: alignment headers only, ~25 % faster
+fullDelta = False      # True: <prefix>.delta holds real MUMmer delta records (indel offset lists; the traceback-recording kernel
+                       # and ~0.6 B of text per query base, about 3x slower end to end).  False (default): rows-only records under a
+                       # `#MFSC rows-only` marker line -- nothing in the reference parses .delta files, show-coords is
+                       # served from the rows
 
 
 def set_engine(E):
@@ -259,6 +262,8 @@ def _load_delta(delta):
         cols = [[] for _ in range(8)]
         cur = None
         for line in f:
+            if line.startswith("#"):
+                continue
             if line.startswith(">"):
                 a = line[1:].split()
                 if a[0] not in rid:

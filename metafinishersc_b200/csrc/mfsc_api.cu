@@ -1481,6 +1481,9 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
   std::vector<char> iobuf(1 << 20);
   setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
   fprintf(f, "%s %s\nNUCMER\n", ref_path, qry_path);
+  if (!deltas)   // not a MUMmer delta: say so where any reader of the file meets it first
+    fprintf(f, "#MFSC rows-only: alignment headers without indel lists, field 7 = alignment columns; "
+               "alignerRobot.fullDelta = True writes MUMmer delta records\n");
   int last_r = -1, last_q = -1;
   for (int64_t i = 0; i < n_rows; i++) {
     if (ref_id[i] != last_r || qry_id[i] != last_q) {

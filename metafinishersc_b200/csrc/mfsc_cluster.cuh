@@ -14,6 +14,8 @@
 #pragma once
 #include "mfsc_seed.cuh"
 
+#define CL_K 4      // members per lane of a component whose chain DP runs as a register wavefront
+
 struct ClusterScratch {
   // per match (slice = the strand's range in the sorted match arrays)
   unsigned* s1; int* s2; int* len; int* rec;  // filtered working copy
@@ -67,6 +69,21 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
     for (int i = lane; i < n; i += MFSC_LANES) { s1[i] = m_s1[b + i]; s2[i] = m_s2[b + i]; len[i] = m_len[b + i]; rec[i] = m_rec[b + i]; flag[i] = 1; }
     wsync();
     // ---- 1. filter ----
+    // The filter only acts on pairs (i, j > i, s2[j] <= end of i) that share a diagonal, a reference start or a query start.
+    // On reads against contigs there is usually no such pair at all: the lanes look for one, each over the windows of its
+    // own matches, and the sequential rule below runs only when one exists.
+    bool any_pair = false;
+    for (int i = lane; i < n - 1; i += MFSC_LANES) {
+      const long long i_s1 = s1[i], i_s2 = s2[i];
+      const long long i_diag = i_s2 - i_s1, i_end = i_s2 + len[i];
+      for (int j = i + 1; j < n && (long long)s2[j] <= i_end; j++) {
+        const long long j_s1 = s1[j], j_s2 = s2[j];
+        if ((j_s2 - j_s1 == i_diag) || j_s1 == i_s1 || j_s2 == i_s2) { any_pair = true; break; }
+      }
+      if (any_pair) break;
+    }
+    int N = n;
+    if (wballot(any_pair) != 0u) {
     for (int i = 0; i < n - 1; i++) {
       unsigned fi = flag[i];
       if (!(fi & 1)) continue;
@@ -121,7 +138,7 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
     }
     wsync();
     // compaction of the surviving matches, in order
-    int N = 0;
+    N = 0;
     for (int i0 = 0; i0 < n; i0 += MFSC_LANES) {
       const int i = i0 + lane;
       const bool keepm = i < n && (flag[i] & 1);
@@ -136,37 +153,31 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
       N += dev_popc32(m);
       wsync();
     }
+    }
     // ---- 2. union-find ----
+    // Pairs closer than maxgap on near diagonals are united; a component's root is its smallest member, whatever the order
+    // of the unions, so the lanes unite concurrently: each takes the windows of its own matches and hooks the larger root
+    // under the smaller one with a compare-and-swap.
     for (int i = lane; i < N; i += MFSC_LANES) uf[i] = -1;
     wsync();
-    for (int i = 0; i < N - 1; i++) {
+    for (int i = lane; i < N - 1; i += MFSC_LANES) {
       const long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
-      for (int j0 = i + 1; j0 < N; j0 += MFSC_LANES) {
-        const int jj = j0 + lane;
-        bool in = false, hit = false;
-        if (jj < N) {
-          const long long sep = (long long)s2[jj] - i_end;
-          in = sep <= P.maxgap;
-          if (in) {
-            const long long dd = ll_abs(((long long)s2[jj] - (long long)s1[jj]) - i_diag);
-            long long lim = (long long)(P.diagfactor * (double)sep);
-            if (lim < P.diagdiff) lim = P.diagdiff;
-            hit = dd <= lim;
-          }
+      for (int j = i + 1; j < N; j++) {
+        const long long sep = (long long)s2[j] - i_end;
+        if (sep > P.maxgap) break;
+        const long long dd = ll_abs(((long long)s2[j] - (long long)s1[j]) - i_diag);
+        long long lim = (long long)(P.diagfactor * (double)sep);
+        if (lim < P.diagdiff) lim = P.diagdiff;
+        if (dd > lim) continue;
+        int a = i, c = j;
+        for (;;) {
+          while (ld_volatile_i32(&uf[a]) >= 0) a = ld_volatile_i32(&uf[a]);
+          while (ld_volatile_i32(&uf[c]) >= 0) c = ld_volatile_i32(&uf[c]);
+          if (a == c) break;
+          const int hi = a > c ? a : c, lo = a > c ? c : a;
+          if (atomic_cas_i32(&uf[hi], -1, lo) == -1) break;
+          a = hi; c = lo;                       // somebody hooked hi meanwhile: walk on from there
         }
-        unsigned m = wballot(hit);
-        if (m) {
-          if (lane == 0) {
-            while (m) {
-              const int j = j0 + dev_ffs32(m) - 1;
-              m &= m - 1u;
-              const int a = uf_find(uf, i), c = uf_find(uf, j);
-              if (a != c) { if (a < c) uf[c] = a; else uf[a] = c; }
-            }
-          }
-          wsync();
-        }
-        if (wballot(in) != all_lanes) break;
       }
     }
     wsync();
@@ -243,6 +254,50 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
           cn = 0;
           break;
         }
+        if (cn <= MFSC_LANES * CL_K) {
+          // Small component (at most CL_K members per lane): the chain DP as a register wavefront.  Lane l holds members
+          // l, l + 32, ...; the members are finished in list order, member j's final score and coordinates are broadcast
+          // from its lane with shuffles and every later member takes j as a candidate -- j ascending and a strict
+          // comparison keep the first best, like the list scan.
+          unsigned m_s1[CL_K]; int m_s2[CL_K], m_len[CL_K], m_a[CL_K], bv[CL_K], bj[CL_K], badj[CL_K];
+#pragma unroll
+          for (int t = 0; t < CL_K; t++) {
+            const int i = lane + MFSC_LANES * t;
+            m_a[t] = -1; m_s1[t] = 0; m_s2[t] = 0; m_len[t] = 0; bv[t] = 0; bj[t] = -1; badj[t] = 0;
+            if (i < cn) { const int a = mem[i]; m_a[t] = a; m_s1[t] = s1[a]; m_s2[t] = s2[a]; m_len[t] = len[a]; bv[t] = m_len[t]; }
+          }
+#pragma unroll
+          for (int tj = 0; tj < CL_K; tj++) {
+            const int jbase = tj * MFSC_LANES;
+            if (jbase < cn - 1) {
+              const int jend = cn - 1 - jbase < MFSC_LANES ? cn - 1 - jbase : MFSC_LANES;
+              for (int o = 0; o < jend; o++) {
+                const int j = jbase + o;
+                const long long sc_j = wbcast_i32(bv[tj], o);
+                const long long j_s1 = wbcast_u32(m_s1[tj], o), j_s2 = wbcast_i32(m_s2[tj], o), j_len = wbcast_i32(m_len[tj], o);
+#pragma unroll
+                for (int t = tj; t < CL_K; t++) {
+                  const int i = lane + MFSC_LANES * t;
+                  if (i > j && i < cn) {
+                    const long long a_s1 = m_s1[t], a_s2 = m_s2[t];
+                    long long olap1 = j_s1 + j_len - a_s1;
+                    long long olap = olap1 > 0 ? olap1 : 0;
+                    long long olap2 = j_s2 + j_len - a_s2;
+                    if (olap2 > olap) olap = olap2;
+                    long long pen = olap + ll_abs((a_s2 - a_s1) - (j_s2 - j_s1));
+                    long long cand = sc_j + m_len[t] - pen;
+                    const int cand32 = cand < -0x40000000ll ? -0x40000000 : (int)cand;
+                    if (cand32 > bv[t]) { bv[t] = cand32; bj[t] = j; badj[t] = (int)olap; }
+                  }
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < CL_K; t++)
+            if (m_a[t] >= 0) { const int a = m_a[t]; score[a] = bv[t]; from[a] = bj[t]; adj[a] = badj[t]; flag[a] = 0; }
+          wsync();
+        } else {
         // chain DP over the members in list order
         for (int i = 0; i < cn; i++) {
           const int a = mem[i];
@@ -272,6 +327,7 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
           }
           wsync();
         }
+        }
         // best chain end: first maximum
         long long key = -1;
         for (int i = lane; i < cn; i += MFSC_LANES) {
@@ -287,32 +343,50 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
         wsync();
         total = wbcast_i64(total, 0);
         if (total >= P.mincluster) {
-          // emit (lane 0), splitting at record changes; overlaps are trimmed off the later match
-          int add_cm = 0, add_pc = 0;
-          if (lane == 0) {
-            bool firstm = true;
-            int lastrec = -1;
-            for (int i = 0; i < cn; i++) {
-              const int a = mem[i];
-              if (!flag[a]) continue;
-              int ad = firstm ? 0 : adj[a];
-              firstm = false;
-              int l = len[a] - ad;
-              if (l <= 0) continue;
-              int w = b + n_cm + add_cm;
-              O.s1[w] = s1[a] + (unsigned)ad; O.s2[w] = s2[a] + ad; O.len[w] = l;
-              if (rec[a] != lastrec) {
-                int pcw = b + n_pc + add_pc;
-                O.pc_first[pcw] = w; O.pc_n[pcw] = 0; O.pc_rec[pcw] = rec[a];
-                add_pc++;
-                lastrec = rec[a];
-              }
-              O.pc_n[b + n_pc + add_pc - 1]++;
-              add_cm++;
+          // emit, splitting at record changes; overlaps are trimmed off the later match.  32 members at a time: the chain
+          // members of a chunk find their output slots with ballots, a member whose record differs from the previous emitted
+          // one opens a split cluster and counts its run inside the chunk, a run that goes on in the next chunk is added there.
+          int add_cm = 0, add_pc = 0, lastrec = -1, open_pc = -1;
+          bool seen_first = false;
+          for (int i0 = 0; i0 < cn; i0 += MFSC_LANES) {
+            const int i = i0 + lane;
+            const int a = i < cn ? mem[i] : 0;
+            const bool kept = i < cn && flag[a];
+            const unsigned mk = wballot(kept);
+            if (mk == 0u) continue;
+            const int first_here = seen_first ? -1 : dev_ffs32(mk) - 1;     // the first member of the chain keeps its whole length
+            seen_first = true;
+            const int ad = kept ? (lane == first_here ? 0 : adj[a]) : 0;
+            const int l = kept ? len[a] - ad : 0;
+            const bool emit = kept && l > 0;
+            const unsigned me = wballot(emit);
+            if (me == 0u) continue;
+            const int myrec = emit ? rec[a] : 0;
+            const unsigned below = me & lt_mask;
+            const int prevlane = below ? 31 - dev_clz32(below) : -1;
+            const int prevrec_sh = wshfl_i32(myrec, prevlane < 0 ? 0 : prevlane);
+            const int prevrec = prevlane >= 0 ? prevrec_sh : lastrec;
+            const bool newpc = emit && myrec != prevrec;
+            const unsigned mp = wballot(newpc);
+            const int w = b + n_cm + add_cm + dev_popc32(me & lt_mask);
+            if (emit) { O.s1[w] = s1[a] + (unsigned)ad; O.s2[w] = s2[a] + ad; O.len[w] = l; }
+            if (newpc) {
+              const int pcw = b + n_pc + add_pc + dev_popc32(mp & lt_mask);
+              const unsigned above = mp & ~lt_mask & ~(1u << lane);
+              const int end = above ? dev_ffs32(above) - 1 : MFSC_LANES;
+              const unsigned upto = end >= 32 ? 0xffffffffu : ((1u << end) - 1u);
+              O.pc_first[pcw] = w; O.pc_rec[pcw] = myrec; O.pc_n[pcw] = dev_popc32(me & upto & ~lt_mask);
             }
+            const int firstp = mp ? dev_ffs32(mp) - 1 : MFSC_LANES;
+            const int carry = dev_popc32(me & (firstp >= 32 ? 0xffffffffu : ((1u << firstp) - 1u)));
+            if (carry && lane == 0) O.pc_n[open_pc] += carry;
+            wsync();
+            if (mp) open_pc = b + n_pc + add_pc + dev_popc32(mp) - 1;
+            add_pc += dev_popc32(mp); add_cm += dev_popc32(me);
+            lastrec = wbcast_i32(myrec, 31 - dev_clz32(me));
           }
-          n_cm += wbcast_i32(add_cm, 0);
-          n_pc += wbcast_i32(add_pc, 0);
+          n_cm += add_cm;
+          n_pc += add_pc;
         }
         // remove the chain: in-order compaction of the members left, 32 at a time
         int w = 0;

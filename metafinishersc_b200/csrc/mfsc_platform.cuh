@@ -67,6 +67,9 @@ static inline unsigned long long atomic_add_u64(unsigned long long* p, unsigned 
 }
 static inline int atomic_add_i32(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline int atomic_max_i32(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomic_cas_i32(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
+static inline unsigned wbcast_u32(unsigned v, int) { return v; }
+static inline int wshfl_i32(int v, int) { return v; }
 static inline int dev_ffs32(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int dev_ffs64(unsigned long long x) { return x ? __builtin_ctzll(x) + 1 : 0; }
 static inline int dev_clz32(unsigned x) { return x ? __builtin_clz(x) : 32; }
@@ -80,6 +83,7 @@ static inline unsigned long long dev_brev64(unsigned long long x) {
   return r;
 }
 static inline unsigned ld_volatile_u32(const volatile unsigned* p) { return *p; }
+static inline int ld_volatile_i32(const volatile int* p) { return *p; }
 static inline unsigned long long ld_volatile_u64(const volatile unsigned long long* p) { return *p; }
 static inline void st_volatile_u64(volatile unsigned long long* p, unsigned long long v) { *p = v; }
 static inline void dev_threadfence() {}
@@ -130,6 +134,9 @@ MFSC_DEV unsigned atomic_add_u32(unsigned* p, unsigned v) { return atomicAdd(p, 
 MFSC_DEV unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 MFSC_DEV int atomic_add_i32(int* p, int v) { return atomicAdd(p, v); }
 MFSC_DEV int atomic_max_i32(int* p, int v) { return atomicMax(p, v); }
+MFSC_DEV int atomic_cas_i32(int* p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+MFSC_DEV unsigned wbcast_u32(unsigned v, int src) { return __shfl_sync(MFSC_FULL, v, src); }
+MFSC_DEV int wshfl_i32(int v, int src) { return __shfl_sync(MFSC_FULL, v, src); }      // per-lane source
 MFSC_DEV int dev_ffs32(unsigned x) { return __ffs((int)x); }
 MFSC_DEV int dev_ffs64(unsigned long long x) { return __ffsll((long long)x); }
 MFSC_DEV int dev_clz32(unsigned x) { return __clz((int)x); }
@@ -139,6 +146,7 @@ MFSC_DEV unsigned dev_byte_rev(unsigned x) { return __byte_perm(x, 0u, 0x0123u);
 MFSC_DEV unsigned dev_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
 MFSC_DEV unsigned long long dev_brev64(unsigned long long x) { return __brevll(x); }
 MFSC_DEV unsigned ld_volatile_u32(const volatile unsigned* p) { return *p; }
+MFSC_DEV int ld_volatile_i32(const volatile int* p) { return *p; }
 MFSC_DEV unsigned long long ld_volatile_u64(const volatile unsigned long long* p) { return *p; }
 MFSC_DEV void st_volatile_u64(volatile unsigned long long* p, unsigned long long v) { *p = v; }
 MFSC_DEV void dev_threadfence() { __threadfence(); }

@@ -84,6 +84,38 @@ def part_boundaries(names, seqs, n_parts, line_len=60):
 
 
 def part_boundaries_len(name_lens, seq_lens, n_parts, line_len=60):
+    """fasta-splitter.pl:160-183 on arrays.  The Perl loop opens a new part in front of record i (when the current part already
+    holds a record) as soon as  total_i > part_end  and  total_i - part_end > part_end - total_{i-1},  total_i being the
+    bytes written up to and including record i; with integer totals and part_end that is  total_i + total_{i-1} > 2 part_end,
+    so every part boundary is one binary search over that (ascending) sum instead of a Python loop over all records."""
+    name_lens = np.asarray(name_lens, dtype=np.int64)
+    seq_lens = np.asarray(seq_lens, dtype=np.int64)
+    n = len(seq_lens)
+    if n == 0:
+        return []
+    lines = (seq_lens + line_len - 1) // line_len if line_len else np.ones(n, dtype=np.int64)
+    sizes = seq_lens + name_lens + 1 + (1 + lines)
+    tot = np.cumsum(sizes)
+    total = int(tot[-1])
+    pair = tot.copy()
+    pair[1:] += tot[:-1]                     # total_i + total_{i-1}
+    parts, begin, part = [], 0, 1
+    while True:
+        part_end = int(total / n_parts * part) + 1
+        # first record i > begin with pair[i] > 2 * part_end
+        i = int(np.searchsorted(pair, 2 * part_end, side="right"))
+        if i <= begin:
+            i = begin + 1
+        if i >= n:
+            parts.append((begin, n))
+            return parts
+        parts.append((begin, i))
+        begin = i
+        part += 1
+
+
+def _part_boundaries_loop(name_lens, seq_lens, n_parts, line_len=60):
+    """The Perl loop spelled out record by record (kept as the checker of part_boundaries_len in tests/)."""
     def seq_size(nlen, slen):
         return slen + nlen + 1 + (1 + ((slen + line_len - 1) // line_len if line_len else 1))
     sizes = [seq_size(int(n), int(s)) for n, s in zip(name_lens, seq_lens)]

@@ -56,6 +56,7 @@ def transliterated_alignSR2LC(dataList, LCLenDic, SRLenDic):
 
 def run_pipeline(engine, oracle, tmp_path):
     alignerRobot.set_engine(engine)
+    alignerRobot.fullDelta = True           # this test also checks the MUMmer delta records
     folder, d, reads = make_folder(tmp_path)
     cwd = os.getcwd()
     try:
@@ -107,6 +108,7 @@ def run_pipeline(engine, oracle, tmp_path):
     alignerRobot.fullDelta = False
     alignerRobot.useMummerAlign("", folder, "hdronly", "LC_filtered.fasta", "SR.part-01.fasta")
     alignerRobot.fullDelta = True
+    assert open(folder + "hdronly.delta").read().split("\n")[2].startswith("#MFSC rows-only")
     alignerRobot.clear_caches()
     alignerRobot.showCoorMummer(False, "", folder, "hdronly", "")
     assert open(folder + "hdronlyOut").read().split("\n")[5:] == text.split("\n")[5:]
@@ -139,6 +141,7 @@ def run_pipeline(engine, oracle, tmp_path):
     # a missing input leaves an empty coords file and an empty row list, like the ignored nucmer failure
     alignerRobot.useMummerAlign("", folder, "nothing", "absent.fasta", "SR.fasta")
     assert alignerRobot.extractMumData(folder, "nothingOut") == []
+    alignerRobot.fullDelta = False
     alignerRobot.set_engine(None)
 
 
