@@ -1000,7 +1000,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     mo.qs = m_qs; mo.s1 = m_s1; mo.s2 = m_s2; mo.len = m_len; mo.rec = m_rec; mo.counter = d_counter; mo.capacity = (unsigned)cap;
     if (rd->n_tiles > 0) {
       // persistent grid: warps take tiles of the query strands from a ticket counter
-      MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, 8), MFSC_LANES * SEED_WARPS, 0, D.stream,
+      MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, 12), MFSC_LANES * SEED_WARPS, 0, D.stream,
                   RS, ix->ostart, ix->view(), QS, ST, P, mo);
       D.launches++;
     }

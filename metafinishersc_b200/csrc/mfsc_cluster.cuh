@@ -14,6 +14,7 @@
 #pragma once
 #include "mfsc_seed.cuh"
 
+#define CL_WIDE 12   // widest window a single lane scans on its own
 #define CL_K 4      // members per lane of a component whose chain DP runs as a register wavefront
 
 struct ClusterScratch {
@@ -35,6 +36,19 @@ MFSC_DEV int uf_find(int* uf, int a) {
   while (uf[r] >= 0) r = uf[r];
   while (uf[a] >= 0) { int nx = uf[a]; uf[a] = r; a = nx; }
   return r;
+}
+
+// find while other lanes hook roots concurrently: parents only ever move to an ancestor (path halving), roots change
+// only through the compare-and-swap of the caller
+MFSC_DEV int uf_find_shared(int* uf, int a) {
+  for (;;) {
+    const int p = ld_volatile_i32(&uf[a]);
+    if (p < 0) return a;
+    const int g = ld_volatile_i32(&uf[p]);
+    if (g < 0) return p;
+    uf[a] = g;
+    a = g;
+  }
 }
 
 MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
@@ -72,16 +86,23 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
     // The filter only acts on pairs (i, j > i, s2[j] <= end of i) that share a diagonal, a reference start or a query start.
     // On reads against contigs there is usually no such pair at all: the lanes look for one, each over the windows of its
     // own matches, and the sequential rule below runs only when one exists.
-    bool any_pair = false;
-    for (int i = lane; i < n - 1; i += MFSC_LANES) {
+    bool any_pair = false, wide = false;
+    for (int i = lane; i < n - 1 && !wide; i += MFSC_LANES) {
       const long long i_s1 = s1[i], i_s2 = s2[i];
       const long long i_diag = i_s2 - i_s1, i_end = i_s2 + len[i];
-      for (int j = i + 1; j < n && (long long)s2[j] <= i_end; j++) {
+      int j = i + 1;
+      for (; j < n && (long long)s2[j] <= i_end + P.maxgap; j++) {
+        if (j - i > CL_WIDE) { wide = true; break; }
+        if ((long long)s2[j] > i_end) continue;
         const long long j_s1 = s1[j], j_s2 = s2[j];
-        if ((j_s2 - j_s1 == i_diag) || j_s1 == i_s1 || j_s2 == i_s2) { any_pair = true; break; }
+        if ((j_s2 - j_s1 == i_diag) || j_s1 == i_s1 || j_s2 == i_s2) any_pair = true;
       }
-      if (any_pair) break;
     }
+    // wide: some match has more than CL_WIDE later matches within maxgap of its end (many reference records overlap the
+    // read, as in all-vs-all read alignment): the windows are then scanned by the whole warp, 32 matches at a time;
+    // otherwise every lane walks the short windows of its own matches.
+    wide = wballot(wide) != 0u;
+    if (wide) any_pair = true;
     int N = n;
     if (wballot(any_pair) != 0u) {
     for (int i = 0; i < n - 1; i++) {
@@ -160,23 +181,55 @@ MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, c
     // under the smaller one with a compare-and-swap.
     for (int i = lane; i < N; i += MFSC_LANES) uf[i] = -1;
     wsync();
-    for (int i = lane; i < N - 1; i += MFSC_LANES) {
-      const long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
-      for (int j = i + 1; j < N; j++) {
-        const long long sep = (long long)s2[j] - i_end;
-        if (sep > P.maxgap) break;
-        const long long dd = ll_abs(((long long)s2[j] - (long long)s1[j]) - i_diag);
-        long long lim = (long long)(P.diagfactor * (double)sep);
-        if (lim < P.diagdiff) lim = P.diagdiff;
-        if (dd > lim) continue;
-        int a = i, c = j;
-        for (;;) {
-          while (ld_volatile_i32(&uf[a]) >= 0) a = ld_volatile_i32(&uf[a]);
-          while (ld_volatile_i32(&uf[c]) >= 0) c = ld_volatile_i32(&uf[c]);
-          if (a == c) break;
-          const int hi = a > c ? a : c, lo = a > c ? c : a;
-          if (atomic_cas_i32(&uf[hi], -1, lo) == -1) break;
-          a = hi; c = lo;                       // somebody hooked hi meanwhile: walk on from there
+    if (!wide) {
+      for (int i = lane; i < N - 1; i += MFSC_LANES) {
+        const long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
+        for (int j = i + 1; j < N; j++) {
+          const long long sep = (long long)s2[j] - i_end;
+          if (sep > P.maxgap) break;
+          const long long dd = ll_abs(((long long)s2[j] - (long long)s1[j]) - i_diag);
+          long long lim = (long long)(P.diagfactor * (double)sep);
+          if (lim < P.diagdiff) lim = P.diagdiff;
+          if (dd > lim) continue;
+          int a = i, c = j;
+          for (;;) {
+            a = uf_find_shared(uf, a); c = uf_find_shared(uf, c);
+            if (a == c) break;
+            const int hi = a > c ? a : c, lo = a > c ? c : a;
+            if (atomic_cas_i32(&uf[hi], -1, lo) == -1) break;
+            a = hi; c = lo;                       // somebody hooked hi meanwhile: walk on from there
+          }
+        }
+      }
+    } else {
+      for (int i = 0; i < N - 1; i++) {
+        const long long i_end = (long long)s2[i] + len[i], i_diag = (long long)s2[i] - (long long)s1[i];
+        for (int j0 = i + 1; j0 < N; j0 += MFSC_LANES) {
+          const int jj = j0 + lane;
+          bool in = false, hit = false;
+          if (jj < N) {
+            const long long sep = (long long)s2[jj] - i_end;
+            in = sep <= P.maxgap;
+            if (in) {
+              const long long dd = ll_abs(((long long)s2[jj] - (long long)s1[jj]) - i_diag);
+              long long lim = (long long)(P.diagfactor * (double)sep);
+              if (lim < P.diagdiff) lim = P.diagdiff;
+              hit = dd <= lim;
+            }
+          }
+          unsigned m = wballot(hit);
+          if (m) {
+            if (lane == 0) {
+              while (m) {
+                const int j = j0 + dev_ffs32(m) - 1;
+                m &= m - 1u;
+                const int a = uf_find(uf, i), c = uf_find(uf, j);
+                if (a != c) { if (a < c) uf[c] = a; else uf[a] = c; }
+              }
+            }
+            wsync();
+          }
+          if (wballot(in) != all_lanes) break;
         }
       }
     }

@@ -61,6 +61,7 @@ MFSC_DEV unsigned mem_slot(unsigned* ctr) {
 #define SEED_HEAVY 8
 #define SEED_LONG 256
 #define SEED_WARPS 4                          // warps per block
+#define SEED_LIST (2 * MFSC_LANES * SEED_U)    // the probes with candidates of up to two rounds wait here, so that the lanes that verify are full
 
 struct SeedTiles {
   const unsigned* tile_off;   // [n_qs + 1] first tile of every query strand (a strand of len bases has ceil(len / 2048) tiles)
@@ -71,7 +72,7 @@ struct SeedTiles {
 struct SeedShared {
   unsigned long long txt[SEED_STAGE];
   unsigned inv[SEED_STAGE];
-  unsigned l_b0[MFSC_LANES * SEED_U]; unsigned l_b1[MFSC_LANES * SEED_U]; int l_p[MFSC_LANES * SEED_U];     // probes with candidates
+  unsigned l_b0[SEED_LIST]; unsigned l_b1[SEED_LIST]; int l_p[SEED_LIST];     // probes with candidates: light buckets from the bottom, heavy ones from the top
   unsigned g_r[MFSC_LANES * 2]; int g_p[MFSC_LANES * 2]; int g_left[MFSC_LANES * 2]; int g_right[MFSC_LANES * 2];   // long matches
 };
 
@@ -223,6 +224,7 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
         }
       }
       wsync();
+      int n_light = 0, n_heavy = 0;                // probes waiting in the shared list (all of this tile)
       for (int i0 = pb; i0 < pe; i0 += MFSC_LANES * SEED_U) {
         // b. SEED_U probes per lane: k-mer, occupancy bit, bucket bounds of the occupied ones
         unsigned long long km[SEED_U]; bool live[SEED_U]; unsigned b0[SEED_U], b1[SEED_U];
@@ -251,8 +253,8 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
             b0[u] = ldg(&X.heads[r]); b1[u] = ldg(&X.heads[r + 1]);
           }
         }
-        // c. probes with candidates -> shared list (light buckets first, heavy ones from the top)
-        int n_light = 0, n_heavy = 0;
+        // c. probes with candidates -> shared list (light buckets from the bottom, heavy ones from the top); the list is
+        //    worked off when another round might not fit, and at the end of the tile
 #pragma unroll
         for (int u = 0; u < SEED_U; u++) {
           const unsigned cnt = b1[u] - b0[u];
@@ -260,10 +262,11 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
           const unsigned ml = wballot(lt), mh = wballot(hv);
           const int p = (i0 + u * MFSC_LANES + lane) * s;
           if (lt) { const int w = n_light + dev_popc32(ml & lt_mask); S.l_b0[w] = b0[u]; S.l_b1[w] = b1[u]; S.l_p[w] = p; }
-          if (hv) { const int w = MFSC_LANES * SEED_U - 1 - n_heavy - dev_popc32(mh & lt_mask); S.l_b0[w] = b0[u]; S.l_b1[w] = b1[u]; S.l_p[w] = p; }
+          if (hv) { const int w = SEED_LIST - 1 - n_heavy - dev_popc32(mh & lt_mask); S.l_b0[w] = b0[u]; S.l_b1[w] = b1[u]; S.l_p[w] = p; }
           n_light += dev_popc32(ml); n_heavy += dev_popc32(mh);
         }
         if (n_light + n_heavy == 0) continue;
+        if (i0 + MFSC_LANES * SEED_U < pe && n_light + n_heavy <= SEED_LIST - MFSC_LANES * SEED_U) continue;
         wsync();
         int n_long = 0;
         // light buckets: one probe per lane
@@ -295,7 +298,7 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
         }
         // heavy buckets: the warp walks one bucket at a time
         for (int y = 0; y < n_heavy; y++) {
-          const int e = MFSC_LANES * SEED_U - 1 - y;
+          const int e = SEED_LIST - 1 - y;
           const unsigned hb = S.l_b0[e], he = S.l_b1[e]; const int p = S.l_p[e];
           for (unsigned h0 = hb; h0 < he; h0 += MFSC_LANES) {
             const unsigned h = h0 + (unsigned)lane;
@@ -326,6 +329,7 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
           const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
           if (lane == 0) seed_emit(C, gr, gp, gl, tot);
         }
+        n_light = 0; n_heavy = 0;
         wsync();
       }
     }
