@@ -985,8 +985,9 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     n_probes += len >= P.k ? (len - P.k) / P.stride + 1 : 0;
   }
   DA(unsigned, d_counter, 8);
+  DA(unsigned long long, d_found, 1);
   long long cap = std::max<long long>(1 << 16, rd->q.n_bases / 16);
-  MemOut mo; unsigned found = 0;
+  MemOut mo; unsigned long long found = 0;
   int *m_qs = nullptr, *m_s2 = nullptr, *m_len = nullptr, *m_rec = nullptr; unsigned* m_s1 = nullptr;
   SeedTiles ST; ST.tile_off = rd->tile_off; ST.n_tiles = rd->n_tiles; ST.ticket = d_counter + 4;
   for (int attempt = 0; attempt < 3; attempt++) {
@@ -997,14 +998,19 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (matches)");
     }
     D.zero(d_counter, sizeof(unsigned) * 8);
-    mo.qs = m_qs; mo.s1 = m_s1; mo.s2 = m_s2; mo.len = m_len; mo.rec = m_rec; mo.counter = d_counter; mo.capacity = (unsigned)cap;
+    D.zero(d_found, sizeof(unsigned long long));
+    mo.qs = m_qs; mo.s1 = m_s1; mo.s2 = m_s2; mo.len = m_len; mo.rec = m_rec; mo.counter = d_found; mo.capacity = (unsigned long long)cap;
     if (rd->n_tiles > 0) {
       // persistent grid: warps take tiles of the query strands from a ticket counter
-      MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, 12), MFSC_LANES * SEED_WARPS, 0, D.stream,
+      MFSC_LAUNCH(k_seeds, grid_for(D, ((long long)rd->n_tiles + 3) / 4 * MFSC_LANES, MFSC_LANES * SEED_WARPS, SEED_BLOCKS_PER_SM), MFSC_LANES * SEED_WARPS, 0, D.stream,
                   RS, ix->ostart, ix->view(), QS, ST, P, mo);
       D.launches++;
     }
-    D.d2h(&found, d_counter, sizeof(unsigned));
+    D.d2h(&found, d_found, sizeof(unsigned long long));
+    if (found >= 0x7fffffffull) {
+      D.free_(m_qs); D.free_(m_s1); D.free_(m_s2); D.free_(m_len); D.free_(m_rec);
+      cleanup(); delete res; return fail(MFSC_ERR_ARG, "more than 2^31 matches in one batch: split the reads into smaller batches");
+    }
     if ((long long)found <= cap) break;
     D.free_(m_qs); D.free_(m_s1); D.free_(m_s2); D.free_(m_len); D.free_(m_rec);
     m_qs = m_s2 = m_len = m_rec = nullptr; m_s1 = nullptr;
@@ -1012,7 +1018,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
   }
   if (!m_qs) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "match buffer: the retry did not converge"); }
   keep(m_qs); keep(m_s1); keep(m_s2); keep(m_len); keep(m_rec);
-  if ((unsigned long long)found >= 0x7fffffffull) { cleanup(); delete res; return fail(MFSC_ERR_ARG, "more than 2^31 matches in one batch: split the reads into smaller batches"); }
+  if (found >= 0x7fffffffull) { cleanup(); delete res; return fail(MFSC_ERR_ARG, "more than 2^31 matches in one batch: split the reads into smaller batches"); }
   const long long M = found;
   res->n_mems = M;
   res->stats[3] = n_probes; res->stats[4] = M;
@@ -1148,20 +1154,32 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         DA(unsigned char, p_tb, n_warps * TB_DIAGS * DP_SLOTS); DA(unsigned char, p_rev, n_warps * TB_DIAGS); DA(int, p_arena, n_warps * (size_t)arena_ints);
         pool.arena_ints = arena_ints;
         DA(int, x_head, M); DA(int, x_tail, M); DA(int, x_dlb, M); DA(int, x_dle, M);
-        const long long dcap = rd->q.n_bases / 2 + (1 << 20);
-        DA(int, d_delta, dcap); DA(unsigned long long, d_used, 2);
-        D.zero(d_used, sizeof(unsigned long long) * 2);
+        // delta buffer: sized for noisy reads (one indel per two bases); a batch that needs more (all-vs-all read alignment:
+        // many alignments per read) reports how much, and the extension is run once more with that much
+        long long dcap = rd->q.n_bases / 2 + (1 << 20);
+        DA(unsigned long long, d_used, 2);
         pool.tb = p_tb; pool.rev = p_rev; pool.arena = p_arena;
-        DO.buf = d_delta; DO.used = d_used; DO.cap = dcap; DO.n_bad = (unsigned*)(d_used + 1);
         R0.head = x_head; R0.tail = x_tail; R0.dl_begin = x_dlb; R0.dl_end = x_dle;
-        if (!tb_packed) {
-          MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
-        } else {
-          MFSC_LAUNCH((k_extend<true, true>), tbpk_grid, tb_block, tbpk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+        for (int attempt = 0; attempt < 2; attempt++) {
+          int* d_delta = (int*)keep(D.alloc(sizeof(int) * (size_t)(dcap + 1)));
+          if (!d_delta) { cleanup(); delete res; return fail(MFSC_ERR_NOMEM, "out of device memory (delta lists)"); }
+          D.zero(d_used, sizeof(unsigned long long) * 2);
+          D.zero(d_stats, sizeof(unsigned long long) * 8);
+          DO.buf = d_delta; DO.used = d_used; DO.cap = dcap; DO.n_bad = (unsigned*)(d_used + 1);
+          if (!tb_packed) {
+            MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+          } else {
+            MFSC_LAUNCH((k_extend<true, true>), tbpk_grid, tb_block, tbpk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+            D.launches++;
+            ExtIn I2 = I;
+            I2.list = x_retry; I2.n_list = I.n_retry; I2.retry = nullptr; I2.n_retry = nullptr;
+            MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I2, n_reads, P, R0, st, ext_ticket + 1, pool, DO);
+          }
+          unsigned long long used0 = 0;
+          D.d2h(&used0, d_used, sizeof(used0));
+          if ((long long)used0 <= dcap) break;
+          dcap = (long long)used0 + (1 << 16);
           D.launches++;
-          ExtIn I2 = I;
-          I2.list = x_retry; I2.n_list = I.n_retry; I2.retry = nullptr; I2.n_retry = nullptr;
-          MFSC_LAUNCH((k_extend<true, false>), tb_grid, tb_block, tb_smem, D.stream, RS, QS, I2, n_reads, P, R0, st, ext_ticket + 1, pool, DO);
         }
       }
       D.launches++;

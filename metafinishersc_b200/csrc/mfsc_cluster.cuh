@@ -53,7 +53,10 @@ MFSC_DEV int uf_find_shared(int* uf, int a) {
 
 MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
 
-MFSC_KERNEL k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
+#ifndef CL_MINBLOCKS
+#define CL_MINBLOCKS 6
+#endif
+MFSC_KERNEL_LB(128, CL_MINBLOCKS) k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
                       int n_qs, DevParams P, ClusterScratch W, ClusterOut O, unsigned* ticket) {
   const int lane = lane_id();
   // strands are handed out by a ticket counter, 8 at a time: the forward strands carry nearly all matches of a

@@ -23,20 +23,20 @@ struct ProbeChunk { int qs, pb, pe; };
 
 struct MemOut {
   int* qs; unsigned* s1; int* s2; int* len; int* rec;
-  unsigned* counter;       // [0] = matches found (may exceed capacity), [1] = probes with >=1 candidate, [2..3] = candidates (u64)
-  unsigned capacity;
+  unsigned long long* counter;   // matches found (64-bit: it keeps counting past the capacity, the host then retries with a larger buffer)
+  unsigned long long capacity;
 };
 
-MFSC_DEV unsigned mem_slot(unsigned* ctr) {
+MFSC_DEV unsigned long long mem_slot(unsigned long long* ctr) {
 #if defined(MFSC_EMU)
-  return atomic_add_u32(ctr, 1u);
+  return atomic_add_u64(ctr, 1ull);
 #else
   unsigned m = __activemask();
   int leader = __ffs((int)m) - 1;
-  unsigned base = 0;
-  if (lane_id() == leader) base = atomicAdd(ctr, (unsigned)__popc(m));
+  unsigned long long base = 0;
+  if (lane_id() == leader) base = atomicAdd(ctr, (unsigned long long)__popc(m));
   base = __shfl_sync(m, base, leader);
-  return base + (unsigned)__popc(m & ((1u << lane_id()) - 1u));
+  return base + (unsigned long long)__popc(m & ((1u << lane_id()) - 1u));
 #endif
 }
 
@@ -61,7 +61,13 @@ MFSC_DEV unsigned mem_slot(unsigned* ctr) {
 #define SEED_HEAVY 8
 #define SEED_LONG 256
 #define SEED_WARPS 4                          // warps per block
-#define SEED_LIST (2 * MFSC_LANES * SEED_U)    // the probes with candidates of up to two rounds wait here, so that the lanes that verify are full
+#ifndef SEED_ROUNDS_HELD
+#define SEED_ROUNDS_HELD 2
+#endif
+#ifndef SEED_BLOCKS_PER_SM
+#define SEED_BLOCKS_PER_SM 12
+#endif
+#define SEED_LIST (SEED_ROUNDS_HELD * MFSC_LANES * SEED_U)    // the probes with candidates of up to SEED_ROUNDS_HELD rounds wait here, so that the lanes that verify are full
 
 struct SeedTiles {
   const unsigned* tile_off;   // [n_qs + 1] first tile of every query strand (a strand of len bases has ceil(len / 2048) tiles)
@@ -129,7 +135,7 @@ MFSC_DEV void seed_emit(const SeedCtx& C, unsigned r, int p, int left, int right
     }
     if (!unique) return;
   }
-  const unsigned slot = mem_slot(&C.out.counter[0]);
+  const unsigned long long slot = mem_slot(C.out.counter);
   if (slot < C.out.capacity) {
     const int rec = seq_of(C.R.start, C.R.n_seq, s1p);
     C.out.qs[slot] = C.qs;
