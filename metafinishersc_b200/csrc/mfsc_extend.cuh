@@ -366,6 +366,18 @@ MFSC_NOINLINE DpOut dp_engine(const ExtCtx& E, int dir, int a0, int b0, int dirn
       lo = wmax_i32(l2); hi = wmax_i32(h2);      // values read from memory: hand them back as uniform
       if (lane == 0) E.acc_caps++;
     }
+    // Dead tail (same rule as the oracle's engine and the packed engine, see mfsc_extend_pk.cuh)
+    if ((d & 7) == 0 && !forced && FinD + breaklen < N + M && (nhi == M || d - nlo == N)) {
+      int ub = -0x40000000;
+      for (int j = nlo + lane; j <= nhi; j += MFSC_LANES) {
+        const int c = cB[j & DP_SMASK];
+        if (c <= DP_NEG) continue;
+        const int rem_a = N - (d - j), rem_b = M - j;
+        const int v = c + DP_GOOD * (rem_a < rem_b ? rem_a : rem_b);
+        ub = v > ub ? v : ub;
+      }
+      if (wmax_i32(ub) < high) { d++; break; }
+    }
     {
       const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;
       nlo = none ? 1 : (lo > a ? lo : a);

@@ -378,6 +378,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
       lo = wmax_i32(l2); hi = wmax_i32(h2);
       if (lane == 0) E.acc_caps++;
     }
+    if ((d & 7) == 0) {
     if ((d & (PK_PERIOD - 1)) == 0) {
       // Rebase the live words: what this diagonal wrote (nD, nI, its best buffer over [nlo, nhi]) and the best buffer
       // of the previous diagonal over [nlo-1, nhi], the slots the next diagonal reads: each of those is either a cell
@@ -414,6 +415,19 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
         cP[y] = (j <= nhi && vP >= PK_LIVE) ? vP - delta : PK_SENT;
       }
       wsync();
+    }
+    // Dead tail (same rule as the oracle's engine): when the band touches the end of a sequence and no cell of this
+    // anti-diagonal can reach the best score again (a cell gains at most DP_GOOD per remaining base pair), and the far corner is
+    // out of reach within the break length, nothing that is reported can change any more.
+    if (!forced && FinD + breaklen < N + M && (nhi == M || d - nlo == N)) {
+      int ub = -0x40000000;
+      for (int j = nlo + lane; j <= nhi; j += MFSC_LANES) {
+        const int rem_a = N - (d - j), rem_b = M - j;
+        const int v = (cB[j & DP_SMASK] >> PK_SB) + DP_GOOD * (rem_a < rem_b ? rem_a : rem_b);
+        ub = v > ub ? v : ub;
+      }
+      if (wmax_i32(ub) < highF) { d++; break; }
+    }
     }
     {
       const int a = d + 1 - N, t = d + 1 < M ? d + 1 : M;

@@ -382,6 +382,22 @@ EngOut engine(const View& Av, i64 a0, const View& Bv, i64 b0, int dirn, i64 N, i
     while (hi >= nlo && high - mx[hi - nlo] > max_diff) hi--;
     if (lo <= hi && hi - lo + 2 > P.band_cap) st.cap_hits++;
     while (lo <= hi && hi - lo + 2 > P.band_cap) { if (mx[lo - nlo] < mx[hi - nlo]) lo++; else hi--; }
+    // Dead tail.  Once the band touches the end of a sequence it can happen that no cell is able to reach the best score
+    // again: cell (i, j) can gain at most GOOD * min(N - i, M - j) more.  Checked on every 8th anti-diagonal over the cells just
+    // computed; when no cell can, and the walk cannot get to the far corner before the break length runs out
+    // (FinD + breaklen < N + M), the anti-diagonals still to come would change nothing that is reported -- FinD, FinJ and the
+    // finish cell are fixed, `reached` stays false -- so the engine stops here.  This is not MUMmer's loop but an early exit
+    // with the same result; it only lowers the number of cells evaluated (on accurate reads the ~200 anti-diagonals an
+    // extension runs past the end of the read).  The CUDA engines apply the same rule, so `cells` stays comparable.
+    if (!forced && (d & 7) == 0 && FinD + P.breaklen < N + M && (cur.hi == M || d - cur.lo == N)) {
+      i64 ub = (i64)NEG * 4;
+      for (i64 j = cur.lo; j <= cur.hi; j++) {
+        const int v = mx[j - cur.lo];
+        if (v <= NEG) continue;
+        ub = std::max<i64>(ub, (i64)v + GOOD * std::min<i64>(N - (d - j), M - j));
+      }
+      if (ub < high) { rows.push_back(std::move(cur)); d++; break; }
+    }
     nlo = std::max<i64>(lo, d + 1 - N);
     nhi = std::min<i64>(hi + 1, std::min<i64>(d + 1, M));
     if (lo > hi) { nlo = 1; nhi = 0; }

@@ -37,9 +37,10 @@ H = rows[1]
 si, ii, ti = H.index("# Samples"), H.index("Instructions Executed"), H.index("Thread Instructions Executed")
 agg = {}
 k = 0
-for r in rows[2:]:
-    if len(r) <= ti or not r[si].isdigit():
-        continue
+body = [r for r in rows[2:] if len(r) > ti and r[si].isdigit()]
+if len(body) == 2 * len(lines):          # ncu lists the function twice in this view
+    body = body[:len(lines)]
+for r in body:
     key = lines[k] if k < len(lines) else ("?", -1)
     k += 1
     a = agg.setdefault(key, [0, 0, 0])
