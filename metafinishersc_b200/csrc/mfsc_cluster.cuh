@@ -54,7 +54,7 @@ MFSC_DEV int uf_find_shared(int* uf, int a) {
 MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
 
 #ifndef CL_MINBLOCKS
-#define CL_MINBLOCKS 6
+#define CL_MINBLOCKS 10       // 51 registers; measured 3.49 ms (10 blocks) vs 3.64 ms (6 or 8) on cfg 1
 #endif
 MFSC_KERNEL_LB(128, CL_MINBLOCKS) k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
                       int n_qs, DevParams P, ClusterScratch W, ClusterOut O, unsigned* ticket) {

@@ -62,7 +62,7 @@ MFSC_DEV unsigned long long mem_slot(unsigned long long* ctr) {
 #define SEED_LONG 256
 #define SEED_WARPS 4                          // warps per block
 #ifndef SEED_ROUNDS_HELD
-#define SEED_ROUNDS_HELD 2
+#define SEED_ROUNDS_HELD 1        // holding the list over two rounds was measured slower (cfg 1: 4.8 vs 2.7 ms): the larger shared-memory footprint costs L1
 #endif
 #ifndef SEED_BLOCKS_PER_SM
 #define SEED_BLOCKS_PER_SM 12
@@ -282,7 +282,21 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
           if (x < n_light) { h = S.l_b0[x]; he = S.l_b1[x]; p = S.l_p[x]; }
           for (int step = 0; step < SEED_HEAVY; step++) {
             int kind = 0, left = 0, right = 0; unsigned r = 0;
-            if (h < he) { r = pos[h]; kind = seed_candidate(C, r, p, &left, &right); h++; }
+            const bool have = h < he;
+            if (have) r = pos[h];
+            bool owned = false;
+#if MFSC_LANES == 32
+            if (step == 0 && k >= s) {
+              // The list holds the probes in order, so the lane below usually holds the previous probe (p - s).  When that probe's
+              // first candidate is r - s, the s bases left of (r, p) lie inside its exact k-mer match (k >= s): this candidate
+              // extends at least s bases to the left and belongs to an earlier probe -- dropped without touching the reference.
+              const unsigned r_prev = __shfl_up_sync(MFSC_FULL, r, 1);
+              const int p_prev = __shfl_up_sync(MFSC_FULL, p, 1);
+              const bool have_prev = __shfl_up_sync(MFSC_FULL, have ? 1 : 0, 1) != 0;
+              owned = have && lane > 0 && have_prev && p_prev == p - s && r_prev == r - (unsigned)s;
+            }
+#endif
+            if (have) { if (!owned) kind = seed_candidate(C, r, p, &left, &right); h++; }
             if (kind == 2) seed_emit(C, r, p, left, right);
             const unsigned ml = wballot(kind == 1);
             if (ml) {
