@@ -1066,7 +1066,14 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
     W.s1 = w_s1; W.s2 = w_s2; W.len = w_len; W.rec = w_rec; W.score = w_score; W.adj = w_adj; W.from = w_from; W.uf = w_uf;
     W.ord = w_ord; W.tmp = w_tmp; W.flag = w_flag;
     O.s1 = o_s1; O.s2 = o_s2; O.len = o_len; O.pc_first = o_pcf; O.pc_n = o_pcn; O.pc_rec = o_pcr; O.n_pc = o_npc; O.n_cm = o_ncm;
-    MFSC_LAUNCH(k_cluster, grid_for(D, ((long long)n_qs + 7) / 8 * MFSC_LANES, 128, 16), 128, 0, D.stream, s_s1, s_s2, s_len, s_rec, seg, n_qs, P, W, O, d_counter + 5);
+    {
+      // strands per ticket: 8 when there are many more strands than resident warps, fewer on small batches so that every warp slot has work
+      const long long resident = (long long)D.n_sm() * CL_MINBLOCKS * 4;
+      long long per_ticket = n_qs / (resident * 4);
+      per_ticket = per_ticket < 1 ? 1 : (per_ticket > 8 ? 8 : per_ticket);
+      MFSC_LAUNCH(k_cluster, grid_for(D, ((long long)n_qs + per_ticket - 1) / per_ticket * MFSC_LANES, 128, 16), 128, 0, D.stream, s_s1, s_s2, s_len, s_rec, seg,
+                  n_qs, P, W, O, d_counter + 5, (unsigned)per_ticket);
+    }
     D.launches++;
     stamp(D, ts[3]);
 

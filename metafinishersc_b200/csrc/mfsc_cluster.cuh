@@ -57,16 +57,17 @@ MFSC_DEV long long ll_abs(long long x) { return x < 0 ? -x : x; }
 #define CL_MINBLOCKS 10       // 51 registers; measured 3.49 ms (10 blocks) vs 3.64 ms (6 or 8) on cfg 1
 #endif
 MFSC_KERNEL_LB(128, CL_MINBLOCKS) k_cluster(const unsigned* m_s1, const int* m_s2, const int* m_len, const int* m_rec, const int* seg,
-                      int n_qs, DevParams P, ClusterScratch W, ClusterOut O, unsigned* ticket) {
+                      int n_qs, DevParams P, ClusterScratch W, ClusterOut O, unsigned* ticket, unsigned per_ticket) {
   const int lane = lane_id();
-  // strands are handed out by a ticket counter, 8 at a time: the forward strands carry nearly all matches of a
-  // reads-vs-contigs batch, so a static round-robin leaves every other warp without work
+  // strands are handed out by a ticket counter, per_ticket at a time (8 on large batches, 1 when there are fewer strands
+  // than resident warps): the forward strands carry nearly all matches of a reads-vs-contigs batch, so a static
+  // round-robin leaves every other warp without work
   for (;;) {
     unsigned q0 = 0;
-    if (lane == 0) q0 = atomic_add_u32(ticket, 8u);
+    if (lane == 0) q0 = atomic_add_u32(ticket, per_ticket);
     q0 = (unsigned)wbcast_i32((int)q0, 0);
     if (q0 >= (unsigned)n_qs) break;
-    const unsigned q1 = q0 + 8u < (unsigned)n_qs ? q0 + 8u : (unsigned)n_qs;
+    const unsigned q1 = q0 + per_ticket < (unsigned)n_qs ? q0 + per_ticket : (unsigned)n_qs;
   for (unsigned qs = q0; qs < q1; qs++) {
     const int b = seg[qs], e = seg[qs + 1];
     const int n = e - b;
@@ -288,9 +289,8 @@ MFSC_KERNEL_LB(128, CL_MINBLOCKS) k_cluster(const unsigned* m_s1, const int* m_s
     int c0 = 0;
     while (c0 < N) {
       // component = maximal run in ord[] sharing a root (roots are smallest members, runs are ascending)
-      int root = score[ord[c0]];
-      int c1 = c0 + 1;
-      while (c1 < N && score[ord[c1]] == root) c1++;
+      const int root = score[ord[c0]];
+      const int c1 = tmp[root];                 // the counting sort left the end slot of every component at its root
       wsync();
       // members of the component live in ord[c0..c1); work on indices into s1/s2/len
       int cn = c1 - c0;
@@ -310,40 +310,53 @@ MFSC_KERNEL_LB(128, CL_MINBLOCKS) k_cluster(const unsigned* m_s1, const int* m_s
           cn = 0;
           break;
         }
-        if (cn <= MFSC_LANES * CL_K) {
-          // Small component (at most CL_K members per lane): the chain DP as a register wavefront.  Lane l holds members
-          // l, l + 32, ...; the members are finished in list order, member j's final score and coordinates are broadcast
-          // from its lane with shuffles and every later member takes j as a candidate -- j ascending and a strict
-          // comparison keep the first best, like the list scan.
-          unsigned m_s1[CL_K]; int m_s2[CL_K], m_len[CL_K], m_a[CL_K], bv[CL_K], bj[CL_K], badj[CL_K];
+        // Small component (at most CL_K members per lane) whose coordinates, taken relative to its first member, fit 28 bits:
+        // the chain DP as a register wavefront in 32-bit arithmetic.  Lane l holds members l, l + 32, ...; the members are
+        // finished in list order, member j's final score and its (end in the reference, end in the read, diagonal) are
+        // broadcast from its lane with shuffles and every later member takes j as a candidate -- j ascending and a strict
+        // comparison keep the first best, like the list scan.  (|cand| stays below 2^31: score and lengths < 2^28, overlap
+        // < 2^29, diagonal difference < 2^30.)
+        bool small = cn <= MFSC_LANES * CL_K;
+        int m_s1[CL_K], m_s2[CL_K], m_len[CL_K], m_a[CL_K], bv[CL_K], bj[CL_K], badj[CL_K];
+        if (small) {
+          const long long base1 = s1[mem[0]], base2 = s2[mem[0]];
+          bool fits = true;
 #pragma unroll
           for (int t = 0; t < CL_K; t++) {
             const int i = lane + MFSC_LANES * t;
             m_a[t] = -1; m_s1[t] = 0; m_s2[t] = 0; m_len[t] = 0; bv[t] = 0; bj[t] = -1; badj[t] = 0;
-            if (i < cn) { const int a = mem[i]; m_a[t] = a; m_s1[t] = s1[a]; m_s2[t] = s2[a]; m_len[t] = len[a]; bv[t] = m_len[t]; }
+            if (i < cn) {
+              const int a = mem[i];
+              const long long r1 = (long long)s1[a] - base1, r2 = (long long)s2[a] - base2;
+              const int l = len[a];
+              fits = fits && r1 > -(1 << 28) && r1 < (1 << 28) && r2 > -(1 << 28) && r2 < (1 << 28) && l < (1 << 28);
+              m_a[t] = a; m_s1[t] = (int)r1; m_s2[t] = (int)r2; m_len[t] = l; bv[t] = l;
+            }
           }
+          small = wballot(!fits) == 0u;
+        }
+        if (small) {
 #pragma unroll
           for (int tj = 0; tj < CL_K; tj++) {
             const int jbase = tj * MFSC_LANES;
             if (jbase < cn - 1) {
               const int jend = cn - 1 - jbase < MFSC_LANES ? cn - 1 - jbase : MFSC_LANES;
+              const int my_e1 = m_s1[tj] + m_len[tj], my_e2 = m_s2[tj] + m_len[tj], my_dg = m_s2[tj] - m_s1[tj];
               for (int o = 0; o < jend; o++) {
                 const int j = jbase + o;
-                const long long sc_j = wbcast_i32(bv[tj], o);
-                const long long j_s1 = wbcast_u32(m_s1[tj], o), j_s2 = wbcast_i32(m_s2[tj], o), j_len = wbcast_i32(m_len[tj], o);
+                const int sc_j = wbcast_i32(bv[tj], o);
+                const int j_e1 = wbcast_i32(my_e1, o), j_e2 = wbcast_i32(my_e2, o), j_dg = wbcast_i32(my_dg, o);
 #pragma unroll
                 for (int t = tj; t < CL_K; t++) {
                   const int i = lane + MFSC_LANES * t;
                   if (i > j && i < cn) {
-                    const long long a_s1 = m_s1[t], a_s2 = m_s2[t];
-                    long long olap1 = j_s1 + j_len - a_s1;
-                    long long olap = olap1 > 0 ? olap1 : 0;
-                    long long olap2 = j_s2 + j_len - a_s2;
-                    if (olap2 > olap) olap = olap2;
-                    long long pen = olap + ll_abs((a_s2 - a_s1) - (j_s2 - j_s1));
-                    long long cand = sc_j + m_len[t] - pen;
-                    const int cand32 = cand < -0x40000000ll ? -0x40000000 : (int)cand;
-                    if (cand32 > bv[t]) { bv[t] = cand32; bj[t] = j; badj[t] = (int)olap; }
+                    const int olap1 = j_e1 - m_s1[t], olap2 = j_e2 - m_s2[t];
+                    int olap = olap1 > 0 ? olap1 : 0;
+                    olap = olap2 > olap ? olap2 : olap;
+                    const int dd = (m_s2[t] - m_s1[t]) - j_dg;
+                    const int cand = sc_j + m_len[t] - olap - (dd < 0 ? -dd : dd);
+                    const int cand32 = cand < -0x40000000 ? -0x40000000 : cand;
+                    if (cand32 > bv[t]) { bv[t] = cand32; bj[t] = j; badj[t] = olap; }
                   }
                 }
               }

@@ -49,7 +49,9 @@ MFSC_DEV unsigned long long mem_slot(unsigned long long* ctr) {
 //      SEED_U independent loads in flight per lane;
 //   c. the probes that found candidates are compacted into a shared-memory list (ballot + popc) and dealt to the
 //      lanes one probe each, so the lanes verifying candidates are the ones that have any; buckets with more than
-//      SEED_HEAVY positions (repeats) are walked by the whole warp, 32 positions at a time;
+//      SEED_HEAVY positions (repeats) are walked by the whole warp, 32 positions at a time.  Verification is two
+//      phases, each on dense lanes: the left test (most candidates end there), then the survivors, compacted
+//      again, are extended to the right;
 //   d. a match that is still running after SEED_LONG bases is finished by the whole warp, 32 words (1024 bases)
 //      per step -- whole-contig matches of a self-alignment (reference call shapes #2/#3/#5/#7 of SURVEY appendix A).
 // Matches are appended with a warp-aggregated atomic; their order is fixed by the sort that follows.
@@ -100,18 +102,21 @@ struct SeedCtx {
   unsigned qstart; int qlen, qs;
 };
 
-// one candidate (reference position r of a k-mer equal to the probe at p).  Returns 1 when the match has to be
-// finished by the warp (left in *left_o, bases matched so far to the right in *right_o), 0 otherwise.
-MFSC_DEV int seed_candidate(const SeedCtx& C, unsigned r, int p, int* left_o, int* right_o) {
-  const int k = C.P.k, s = C.P.stride;
-  const unsigned qp = C.qstart + (unsigned)p;
-  const int maxl = p < s ? p : s;
-  const int left = match_left(C.R, r, C.Q, qp, maxl);
-  if (left >= s) return 0;                        // an earlier probe owns this match
+// left test of one candidate (reference position r of a k-mer equal to the probe at p): the number of matching bases to the
+// left, at most s; s means "an earlier probe owns this match"
+MFSC_DEV int seed_left(const SeedCtx& C, unsigned r, int p) {
+  const int s = C.P.stride;
+  return match_left(C.R, r, C.Q, C.qstart + (unsigned)p, p < s ? p : s);
+}
+
+// right extension of a candidate that passed the left test, the first SEED_LONG bases: returns 1 when the match is still
+// running (the warp finishes it), 2 when it ended
+MFSC_DEV int seed_right(const SeedCtx& C, unsigned r, int p, int* right_o) {
+  const int k = C.P.k;
   const int lim = C.qlen - p - k;
   const int first = lim < SEED_LONG ? lim : SEED_LONG;
-  const int right = match_right(C.R, r + k, C.Q, qp + k, first);
-  *left_o = left; *right_o = right;
+  const int right = match_right(C.R, r + k, C.Q, C.qstart + (unsigned)(p + k), first);
+  *right_o = right;
   return (right >= first && first < lim) ? 1 : 2;
 }
 
@@ -274,14 +279,39 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
         if (n_light + n_heavy == 0) continue;
         if (i0 + MFSC_LANES * SEED_U < pe && n_light + n_heavy <= SEED_LIST - MFSC_LANES * SEED_U) continue;
         wsync();
-        int n_long = 0;
+        // Verification in two phases, so that each runs on dense lanes.  Phase 1, one candidate per lane: position, left test.
+        // Most candidates end here (inside a match an earlier probe owns, or a chance k-mer hit).  The survivors -- the left
+        // ends of matches -- are compacted into a second list, and phase 2 extends them to the right, one per lane.
+        int n_v = 0;                                 // survivors waiting in S.g_*
+        // phase 2 + 3 over the survivor list
+#define SEED_EXTEND_SURVIVORS()                                                                                       \
+        {                                                                                                              \
+          wsync();                                                                                                     \
+          for (int x0 = 0; x0 < n_v; x0 += MFSC_LANES) {                                                               \
+            const int x = x0 + lane;                                                                                   \
+            int kind = 0, right = 0; unsigned r = 0; int p = 0, left = 0;                                              \
+            if (x < n_v) { r = S.g_r[x]; p = S.g_p[x]; left = S.g_left[x]; kind = seed_right(C, r, p, &right); }       \
+            if (kind == 2) seed_emit(C, r, p, left, right);                                                            \
+            if (x < n_v) S.g_right[x] = kind == 1 ? right : -1;                                                        \
+          }                                                                                                            \
+          wsync();                                                                                                     \
+          for (int g = 0; g < n_v; g++) {                  /* matches still running: the whole warp finishes each */   \
+            const int gright = S.g_right[g];                                                                           \
+            if (gright < 0) continue;                                                                                  \
+            const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];                                   \
+            const int tot = seed_finish_long(C, gr, gp, gright, lane);                                                 \
+            if (lane == 0) seed_emit(C, gr, gp, gl, tot);                                                              \
+          }                                                                                                            \
+          n_v = 0;                                                                                                     \
+          wsync();                                                                                                     \
+        }
         // light buckets: one probe per lane
         for (int x0 = 0; x0 < n_light; x0 += MFSC_LANES) {
           const int x = x0 + lane;
           unsigned h = 0, he = 0; int p = 0;
           if (x < n_light) { h = S.l_b0[x]; he = S.l_b1[x]; p = S.l_p[x]; }
           for (int step = 0; step < SEED_HEAVY; step++) {
-            int kind = 0, left = 0, right = 0; unsigned r = 0;
+            int left = s; unsigned r = 0;
             const bool have = h < he;
             if (have) r = pos[h];
             bool owned = false;
@@ -296,22 +326,13 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
               owned = have && lane > 0 && have_prev && p_prev == p - s && r_prev == r - (unsigned)s;
             }
 #endif
-            if (have) { if (!owned) kind = seed_candidate(C, r, p, &left, &right); h++; }
-            if (kind == 2) seed_emit(C, r, p, left, right);
-            const unsigned ml = wballot(kind == 1);
-            if (ml) {
-              if (kind == 1) { const int w = n_long + dev_popc32(ml & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; S.g_right[w] = right; }
-              n_long += dev_popc32(ml);
-              wsync();
-              if (n_long > MFSC_LANES) {            // keep room for another 32
-                for (int g = 0; g < n_long; g++) {
-                  const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
-                  const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
-                  if (lane == 0) seed_emit(C, gr, gp, gl, tot);
-                }
-                n_long = 0;
-                wsync();
-              }
+            if (have) { if (!owned) left = seed_left(C, r, p); h++; }
+            const bool surv = have && left < s;
+            const unsigned mv = wballot(surv);
+            if (mv) {
+              if (surv) { const int w = n_v + dev_popc32(mv & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; }
+              n_v += dev_popc32(mv);
+              if (n_v > MFSC_LANES) SEED_EXTEND_SURVIVORS()       // keep room for another 32
             }
             if (wballot(h < he) == 0u) break;
           }
@@ -322,33 +343,19 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
           const unsigned hb = S.l_b0[e], he = S.l_b1[e]; const int p = S.l_p[e];
           for (unsigned h0 = hb; h0 < he; h0 += MFSC_LANES) {
             const unsigned h = h0 + (unsigned)lane;
-            int kind = 0, left = 0, right = 0; unsigned r = 0;
-            if (h < he) { r = pos[h]; kind = seed_candidate(C, r, p, &left, &right); }
-            if (kind == 2) seed_emit(C, r, p, left, right);
-            const unsigned ml = wballot(kind == 1);
-            if (ml) {
-              if (kind == 1) { const int w = n_long + dev_popc32(ml & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; S.g_right[w] = right; }
-              n_long += dev_popc32(ml);
-              wsync();
-              if (n_long > MFSC_LANES) {
-                for (int g = 0; g < n_long; g++) {
-                  const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
-                  const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
-                  if (lane == 0) seed_emit(C, gr, gp, gl, tot);
-                }
-                n_long = 0;
-                wsync();
-              }
+            int left = s; unsigned r = 0;
+            if (h < he) { r = pos[h]; left = seed_left(C, r, p); }
+            const bool surv = h < he && left < s;
+            const unsigned mv = wballot(surv);
+            if (mv) {
+              if (surv) { const int w = n_v + dev_popc32(mv & lt_mask); S.g_r[w] = r; S.g_p[w] = p; S.g_left[w] = left; }
+              n_v += dev_popc32(mv);
+              if (n_v > MFSC_LANES) SEED_EXTEND_SURVIVORS()
             }
           }
         }
-        // d. long matches left over
-        wsync();
-        for (int g = 0; g < n_long; g++) {
-          const unsigned gr = S.g_r[g]; const int gp = S.g_p[g], gl = S.g_left[g];
-          const int tot = seed_finish_long(C, gr, gp, S.g_right[g], lane);
-          if (lane == 0) seed_emit(C, gr, gp, gl, tot);
-        }
+        if (n_v > 0) SEED_EXTEND_SURVIVORS()
+#undef SEED_EXTEND_SURVIVORS
         n_light = 0; n_heavy = 0;
         wsync();
       }

@@ -9,7 +9,7 @@ import tempfile
 
 rep, kre, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-so = "metafinishersc_b200/csrc/libmfsc_b200.so"
+so = __import__("os").environ.get("HOTLINES_SO", "metafinishersc_b200/csrc/libmfsc_b200.so")    # the build that was profiled
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(["cuobjdump", "-xelf", "all", __import__("os").path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
     cub = [f for f in __import__("os").listdir(tmp) if f.endswith(".cubin")][0]
