@@ -268,22 +268,34 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
                 "mine": torch.zeros((cap, 8), dtype=torch.int32, device="cuda"), "stage": torch.zeros((4 * cap, 8), dtype=torch.int32).pin_memory(),
                 "list": [torch.zeros((cap, 8), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None}
 
+    n_local = len(off) - 1
+    n_pieces = max(1, min(args.strong_pieces, n_local))
+    cuts = [n_local * k // n_pieces for k in range(n_pieces + 1)]
+
     def one_step():
+        import queue
         parts = {}
         box = {}
+        q = queue.Queue()
 
         def up():
+            # the rank's read batch goes up (and is packed) in pieces on a second host thread / stream, while the index is made
+            # and while the pieces before it are aligned
             try:
                 E2 = engine.Engine(E.L)
                 E2.set_device(local)
-                box["reads"] = E2.upload((hbuf, hoff))
+                for k in range(n_pieces):
+                    lo, hi = cuts[k], cuts[k + 1]
+                    q.put(E2.upload((hbuf[hoff[lo]:hoff[hi]], hoff[lo:hi + 1] - hoff[lo])))
+                box["upload_done"] = time.perf_counter()
                 E2.thread_release()
             except Exception as e:       # surfaced below
                 box["err"] = e
+                q.put(None)
         barrier()
         t0 = time.perf_counter()
         th = threading.Thread(target=up)
-        th.start()                                  # the rank's read batch goes up (and is packed) while the index is made
+        th.start()
         ix = None
         if world > 1 and args.strong_index == "sharded":
             # every rank builds 1/N of the k-mer space, the slices are exchanged over NVLink (mfsc_index_build_sharded)
@@ -299,15 +311,34 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
             if world > 1:
                 ix, _ = comm.broadcast(ix, len(hco) - 1, root=0)
             parts["broadcast_ms"] = (time.perf_counter() - tb) * 1e3 if world > 1 else 0.0
-        th.join()
-        if "err" in box:
-            raise box["err"]
-        parts["upload_done_ms"] = (time.perf_counter() - t0) * 1e3
         ta = time.perf_counter()
-        r = E.align_reads(ix, box["reads"], P)
+        rows_l, stage_ms, wait_ms = [], {}, 0.0
+        for k in range(n_pieces):
+            tw = time.perf_counter()
+            reads_k = q.get()
+            wait_ms += (time.perf_counter() - tw) * 1e3
+            if reads_k is None:
+                raise box["err"]
+            rk = E.align_reads(ix, reads_k, P)
+            reads_k.free()
+            rk.qry_id = rk.qry_id + cuts[k]
+            rows_l.append(rk)
+            for kk, v in rk.ms.items():
+                stage_ms[kk] = stage_ms.get(kk, 0.0) + v
+        th.join()
         parts["align_ms"] = (time.perf_counter() - ta) * 1e3
+        parts["waited_for_uploads_ms"] = wait_ms
+        parts["upload_done_ms"] = (box["upload_done"] - t0) * 1e3
+
+        class _R:
+            pass
+        r = _R()
+        for fld in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            setattr(r, fld, np.concatenate([getattr(x, fld) for x in rows_l]))
+        r.ms = stage_ms
+        n_rows_local = len(r.s1)
         tg = time.perf_counter()
-        n_rows = len(r)
+        n_rows = n_rows_local
         if world > 1:
             # rows to rank 0 in rank order (= the global read order): the counts with one all-gather, then one gather of
             # fixed-size device buffers (capacity: 2 rows per read of the largest shard, grown when a step needs more)
@@ -318,6 +349,7 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
             if max(counts_h) > cap:
                 cap = gbuf["cap"] = 2 * max(counts_h)
                 gbuf["mine"] = torch.zeros((cap, 8), dtype=torch.int32, device="cuda")
+                gbuf["stage"] = torch.zeros((cap, 8), dtype=torch.int32).pin_memory()
                 gbuf["list"] = [torch.zeros_like(gbuf["mine"]) for _ in range(world)] if rank == 0 else None
             if n_rows:
                 gbuf["stage"][:n_rows] = torch.from_numpy(np.stack([r.ref_id, r.qry_id + a, r.s1, r.e1, r.s2, r.e2, r.errors, r.cols], axis=1))
@@ -331,7 +363,6 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
         wall = (time.perf_counter() - t0) * 1e3
         parts["stage_ms"] = dict(r.ms)
         parts["rows_total"] = n_rows
-        box["reads"].free()
         ix.free()
         return wall, parts
 
@@ -352,8 +383,9 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
             "scaling": "strong", "value": bases_total * K / (wall_max * 1e-3) / 1e6, "unit": "Mbp/s", "steps": K, "ms_per_step": wall_max / K,
             "index": ("sharded build: every rank packs the contigs and builds 1/N of the k-mer space, slices exchanged with grouped NCCL broadcasts"
                       if world > 1 and args.strong_index == "sharded" else "built on rank 0, NCCL broadcast of the 5 index buffers") if world > 1 else "built in place",
-            "inside_the_wall": "index (see `index`; from pinned host contigs) + H2D and packing of "
-                               "the rank's reads (second host thread/stream, overlapped with the index build) + stages 2-4 + rows to the "
+            "pieces_per_rank": n_pieces,
+            "inside_the_wall": "index (see `index`; from pinned host contigs) + H2D and packing of the rank's reads in `pieces_per_rank` pieces "
+                               "(second host thread/stream, overlapped with the index build and with the alignment of the pieces before) + stages 2-4 + rows to the "
                                "host + rows gathered on rank 0 in rank order; host clock, barrier both sides, max over ranks",
             "rank0_breakdown_ms": {k: v for k, v in last.items() if k.endswith("_ms")}, "rank0_stage_ms": last["stage_ms"],
             "align_ms_max_over_ranks": align_max, "align_ms_min_over_ranks": align_min, "rows_total": last["rows_total"]}
@@ -418,6 +450,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the sharded cfg3 job")
     ap.add_argument("--no-wrapper", action="store_true", help="skip the file-level alignerRobot.largeRvsQAlign measurement")
     ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--strong-pieces", type=int, default=4, help="sub-batches a rank's reads go up in (upload of piece k+1 overlaps the alignment of piece k)")
     ap.add_argument("--strong-index", default="sharded", choices=["sharded", "broadcast"],
                     help="N > 1: every rank builds 1/N of the index and the slices are exchanged (sharded), or rank 0 builds and broadcasts")
     ap.add_argument("--strong-genome", type=int, default=5_000_000)

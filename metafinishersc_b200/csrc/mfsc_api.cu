@@ -75,10 +75,10 @@ struct Dev {
     return p;
   }
   void free_(void* p) { if (p) cudaFreeAsync(p, stream); }
-  // large uploads go in 32 MB pieces: the copy engine arbitrates between streams per operation, so a small upload of another
+  // large uploads go in 8 MB pieces: the copy engine arbitrates between streams per operation, so a small upload of another
   // stream (the contigs of an index build next to a 1.5 GB read batch) waits for one piece, not for the whole batch
   void h2d(void* d, const void* h, size_t n) {
-    const size_t piece = (size_t)32 << 20;
+    const size_t piece = (size_t)8 << 20;
     for (size_t o = 0; o < n; o += piece) cudaMemcpyAsync((char*)d + o, (const char*)h + o, n - o < piece ? n - o : piece, cudaMemcpyHostToDevice, stream);
   }
   void d2h(void* h, const void* d, size_t n) { if (n) { cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); } }
@@ -570,6 +570,7 @@ struct NcclApi {
   int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -581,7 +582,7 @@ struct NcclApi {
     if (!lib) { err = std::string("NCCL not found: ") + dlerror(); return false; }
 #define MFSC_NCCL_SYM(field, sym) field = (decltype(field))dlsym(lib, sym); if (!field) { err = std::string("NCCL symbol missing: ") + sym; lib = nullptr; return false; }
     MFSC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") MFSC_NCCL_SYM(CommInitRank, "ncclCommInitRank") MFSC_NCCL_SYM(CommInitAll, "ncclCommInitAll")
-    MFSC_NCCL_SYM(CommDestroy, "ncclCommDestroy") MFSC_NCCL_SYM(Broadcast, "ncclBroadcast") MFSC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    MFSC_NCCL_SYM(CommDestroy, "ncclCommDestroy") MFSC_NCCL_SYM(Broadcast, "ncclBroadcast") MFSC_NCCL_SYM(AllGather, "ncclAllGather") MFSC_NCCL_SYM(GroupStart, "ncclGroupStart")
     MFSC_NCCL_SYM(GroupEnd, "ncclGroupEnd") MFSC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef MFSC_NCCL_SYM
     return true;
@@ -877,17 +878,44 @@ int mfsc_index_build_sharded(mfsc_comm* c, const uint8_t* bases, const int64_t* 
     const unsigned np = (unsigned)ix->n_pos;
     D.h2d(ix->heads + ix->n_heads, &np, sizeof(unsigned));
   }
-  // exchange: slice r comes from rank r
-  for (int what = 0; what < 3 && !nrc; what++) {
-    nrc = g_nccl.GroupStart();
-    for (int r = 0; r < N && !nrc; r++) {
-      char* buf; size_t bytes;
-      if (what == 0) { buf = (char*)(ix->dir + word_lo(r)); bytes = sizeof(uint2) * (size_t)(word_lo(r + 1) - word_lo(r)); }
-      else if (what == 1) { buf = (char*)(ix->heads + occ_off[r]); bytes = sizeof(unsigned) * (size_t)sizes[2 * r]; }
-      else { buf = (char*)(ix->pos + pos_off[r]); bytes = sizeof(unsigned) * (size_t)sizes[2 * r + 1]; }
-      if (bytes) nrc = g_nccl.Broadcast(buf, buf, bytes, NCCL_U8, r, c->comms[0], c->streams[0]);
+  // exchange: slice r comes from rank r.  The directory slices have equal size: one in-place ncclAllGather.  Heads and positions
+  // are (nearly) equal pieces of different size: each is gathered with one ncclAllGather into a staging buffer of N x the
+  // largest piece and copied into place.
+  {
+    const long long wpr = words / N;
+    if (words % N == 0 && wpr > 0) {
+      nrc = g_nccl.AllGather(ix->dir + word_lo(me), ix->dir, sizeof(uint2) * (size_t)wpr, NCCL_U8, c->comms[0], c->streams[0]);
+    } else {
+      nrc = g_nccl.GroupStart();
+      for (int r = 0; r < N && !nrc; r++) {
+        const size_t bytes = sizeof(uint2) * (size_t)(word_lo(r + 1) - word_lo(r));
+        if (bytes) nrc = g_nccl.Broadcast(ix->dir + word_lo(r), ix->dir + word_lo(r), bytes, NCCL_U8, r, c->comms[0], c->streams[0]);
+      }
+      int e2 = g_nccl.GroupEnd(); if (!nrc) nrc = e2;
     }
-    int e2 = g_nccl.GroupEnd(); if (!nrc) nrc = e2;
+    long long max_occ = 0, max_pos = 0;
+    for (int r = 0; r < N; r++) { max_occ = std::max(max_occ, sizes[2 * r]); max_pos = std::max(max_pos, sizes[2 * r + 1]); }
+    unsigned* st_h = dalloc<unsigned>(D, (size_t)max_occ * N + 1);
+    unsigned* st_p = dalloc<unsigned>(D, (size_t)max_pos * N + 1);
+    if (!st_h || !st_p) { D.free_(st_h); D.free_(st_p); slice_free(D, S); index_release(D, ix); return fail(MFSC_ERR_NOMEM, "out of device memory (exchange)"); }
+    if (!nrc && max_occ) {
+      cudaMemcpyAsync(st_h + (size_t)max_occ * me, ix->heads + occ_off[me], sizeof(unsigned) * (size_t)sizes[2 * me], cudaMemcpyDeviceToDevice, D.stream);
+      nrc = g_nccl.AllGather(st_h + (size_t)max_occ * me, st_h, sizeof(unsigned) * (size_t)max_occ, NCCL_U8, c->comms[0], c->streams[0]);
+      for (int r = 0; r < N; r++)
+        if (r != me && sizes[2 * r]) cudaMemcpyAsync(ix->heads + occ_off[r], st_h + (size_t)max_occ * r, sizeof(unsigned) * (size_t)sizes[2 * r], cudaMemcpyDeviceToDevice, D.stream);
+    }
+    if (!nrc && max_pos) {
+      cudaMemcpyAsync(st_p + (size_t)max_pos * me, ix->pos + pos_off[me], sizeof(unsigned) * (size_t)sizes[2 * me + 1], cudaMemcpyDeviceToDevice, D.stream);
+      nrc = g_nccl.AllGather(st_p + (size_t)max_pos * me, st_p, sizeof(unsigned) * (size_t)max_pos, NCCL_U8, c->comms[0], c->streams[0]);
+      for (int r = 0; r < N; r++)
+        if (r != me && sizes[2 * r + 1]) cudaMemcpyAsync(ix->pos + pos_off[r], st_p + (size_t)max_pos * r, sizeof(unsigned) * (size_t)sizes[2 * r + 1], cudaMemcpyDeviceToDevice, D.stream);
+    }
+    {
+      const unsigned np = (unsigned)ix->n_pos;       // the terminal entry again: rank N-1's piece may have been copied over it
+      D.h2d(ix->heads + ix->n_heads, &np, sizeof(unsigned));
+    }
+    D.sync();
+    D.free_(st_h); D.free_(st_p);
   }
   D.sync();
   slice_free(D, S);
