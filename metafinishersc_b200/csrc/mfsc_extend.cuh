@@ -603,6 +603,7 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
       }
     }
     const int nm = c_nm(E, cur), dir = c_dir(E, cur);
+    int tl_ok = 0, tl_cols = 0, tl_errs = 0, tl_chunk = -1;          // this lane's small rectangle of the current chunk of gaps
     for (int mi = 0; mi < nm; mi++) {
       const int ms1 = c_s1(E, cur, mi), ms2 = c_s2(E, cur, mi), mlen = c_len(E, cur, mi);
       if (target_reached) {
@@ -628,7 +629,39 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
       }
       if (mi < nm - 1) {
         tA = c_s1(E, cur, mi + 1); tB = c_s2(E, cur, mi + 1);
-        target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, false);
+        bool taken = false;
+        if (PK && !TB) {
+          // the gaps of this cluster, 32 at a time, one small rectangle per lane (dp_tiny_lane)
+          if (tl_chunk != mi / MFSC_LANES) {          // (a chunk's first gap may have been skipped by the walk: go by chunk, not by mi)
+            tl_chunk = mi / MFSC_LANES;
+            const int g = tl_chunk * MFSC_LANES + E.lane;
+            tl_ok = 0;
+            if (g < nm - 1) {
+              const int gA = c_s1(E, cur, g) + c_len(E, cur, g) - 1, gB = c_s2(E, cur, g) + c_len(E, cur, g) - 1;
+              const int gN = c_s1(E, cur, g + 1) - gA + 1, gM = c_s2(E, cur, g + 1) - gB + 1;
+              if (gN >= 1 && gM >= 1 && gN <= TL_MAX && gM <= TL_MAX && gN + gM <= pk_tiny_limit(E.P.breaklen, E.P.band_cap))
+                tl_ok = dp_tiny_lane(E, dir, gA, gB, gN, gM, &tl_cols, &tl_errs) ? 1 : 0;
+            }
+          }
+          const int src = mi % MFSC_LANES;
+          const int ok = wbcast_i32(tl_ok, src), gcols = wbcast_i32(tl_cols, src), gerrs = wbcast_i32(tl_errs, src);
+          const int eA = E.R.eA[curA], eB = E.R.eB[curA];
+          if (ok && !E.pk_fail && eA == ms1 + mlen - 1 && eB == ms2 + mlen - 1) {
+            const int gN = tA - eA + 1, gM = tB - eB + 1;
+            wsync();
+            if (E.lane == 0) {
+              E.R.cols[curA] += gcols - 1; E.R.errs[curA] += gerrs;
+              E.R.eA[curA] = tA; E.R.eB[curA] = tB;
+              E.acc_cells += (unsigned long long)(gN + 1) * (unsigned long long)(gM + 1) - 1ull; E.acc_calls += 1ull;
+              const int mw = (gN < gM ? gN : gM) + 1;
+              if (mw > E.acc_maxw) E.acc_maxw = mw;
+            }
+            wsync();
+            target_reached = true;
+            taken = true;
+          }
+        }
+        if (!taken) target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, false);
       } else {
         tA = E.A.n; tB = E.B[0].n;
         targetC = ext_forward_target(E, cur, tA, tB);

@@ -213,6 +213,53 @@ MFSC_DEV DpOut dp_engine_tiny(const ExtCtx& E, int dir, int a0, int b0, int dirn
   return o;
 }
 
+// ------------------------------------------------------------------------------------------
+// small rectangles, one per LANE
+// ------------------------------------------------------------------------------------------
+// On accurate reads most DP calls are the gaps between consecutive matches of a cluster: one or two differing bases, a
+// rectangle of a few bases a side.  Their start cell is the end of the match before them and their target the start of the
+// next match -- both known from the cluster alone -- so the gaps of a cluster do not wait for one another: the lanes fill 32
+// of them at a time, each lane its own rectangle with the same packed cell, the same initial words and the same sentinel
+// borders as dp_engine_tiny, in registers / local memory.  The walk (ext_clusters) then takes the finished (columns, errors)
+// where it would have called the warp-wide engine; anything that does not fit (sides over TL_MAX, a base that is not ACGT,
+// delta mode) takes the normal call.
+#define TL_MAX 7
+#define TL_SLOTS (TL_MAX + 3)
+
+MFSC_DEV bool dp_tiny_lane(const ExtCtx& E, int dir, int a0, int b0, int N, int M, int* cols, int* errs) {
+  constexpr bool TB = false;
+  const DevParams& P = E.P;
+  const int one = P.one, kclean = P.pk_clean, kprio = P.pk_prio;
+  unsigned long long ac = 0, bc = 0;      // 3 bits per base
+  bool bad = false;
+  for (int t = 0; t < N; t++) { const int c = code_at(E.RS, E.A.base + (unsigned)(a0 + t - 1)); bad |= c > 3; ac |= (unsigned long long)c << (3 * t); }
+  for (int t = 0; t < M; t++) { const int c = code_at(E.QS, E.B[dir].base + (unsigned)(b0 + t - 1)); bad |= c > 3; bc |= (unsigned long long)c << (3 * t); }
+  if (bad) return false;
+  int nD[TL_SLOTS], nI[TL_SLOTS], B0[TL_SLOTS], B1[TL_SLOTS];     // slot j + 1 holds column j, j = -1 .. M + 1
+#pragma unroll
+  for (int y = 0; y < TL_SLOTS; y++) { nD[y] = PK_SENT; nI[y] = PK_SENT; B0[y] = PK_SENT; B1[y] = PK_SENT; }
+  nD[1] = (PK_H0 + DP_GOPEN) * PK_K + PK_U1; nI[1] = ((PK_H0 + DP_GOPEN) * PK_K) | PK_P;
+  B0[1] = PK_H0 * PK_K;
+  for (int d = 1; d <= N + M; d++) {
+    const int lo = d - N > 0 ? d - N : 0, hi = d < M ? d : M;
+    int* cB = (d & 1) ? B1 : B0;
+    for (int j = hi; j >= lo; j--) {          // descending: every input is read before the cell that overwrites it
+      const int i = d - j;
+      const int sD = nD[j], sI = nI[j + 1], sB = cB[j];
+      const unsigned ca = i >= 1 ? (unsigned)((ac >> (3 * (i - 1))) & 7ull) : 4u, cb = j >= 1 ? (unsigned)((bc >> (3 * (j - 1))) & 7ull) : 5u;
+      const unsigned xm = ca ^ cb;
+      int ob, od, oi; unsigned ot = 0;
+      PK_CELL(0, sD, sI, sB, ob, od, oi, ot)
+      (void)ot;
+      cB[j + 1] = ob; nD[j + 1] = od; nI[j + 1] = oi;
+    }
+  }
+  const int cw = (((N + M) & 1) ? B1 : B0)[M + 1];
+  const int u = PK_UF(cw), mm = PK_MF(cw);
+  *cols = N + u; *errs = mm + N - M + 2 * u;
+  return true;
+}
+
 // Returns what dp_engine returns.  When a rebase finds a field out of range E.pk_fail is set and the result is void.
 template <bool TB>
 MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int dirn, int N_, int M_, bool forced_, bool optimal, bool want_ops) {
