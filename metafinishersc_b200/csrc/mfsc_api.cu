@@ -1224,8 +1224,10 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       int total = 0;
       D.d2h(&total, r_off + n_reads, sizeof(int));
       n_rows = total;
-      DA(int, c_ref, n_rows); DA(int, c_qry, n_rows); DA(int, c_dir, n_rows); DA(int, c_sA, n_rows); DA(int, c_eA, n_rows); DA(int, c_sB, n_rows);
-      DA(int, c_eB, n_rows); DA(int, c_errs, n_rows); DA(int, c_cols, n_rows);
+      // the eight row columns sit in one buffer, so that they come back with one copy
+      DA(int, c_all, 8 * (size_t)n_rows); DA(int, c_dir, n_rows);
+      int* c_ref = c_all; int* c_qry = c_all + n_rows; int* c_sA = c_all + 2 * (size_t)n_rows; int* c_eA = c_all + 3 * (size_t)n_rows;
+      int* c_sB = c_all + 4 * (size_t)n_rows; int* c_eB = c_all + 5 * (size_t)n_rows; int* c_errs = c_all + 6 * (size_t)n_rows; int* c_cols = c_all + 7 * (size_t)n_rows;
       int *c_dlb = nullptr, *c_dle = nullptr;
       if (want_deltas) {
         c_dlb = (int*)keep(D.alloc(sizeof(int) * (size_t)(n_rows + 1))); c_dle = (int*)keep(D.alloc(sizeof(int) * (size_t)(n_rows + 1)));
@@ -1237,10 +1239,12 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       D.launches++;
       res->ref.resize(n_rows); res->qry.resize(n_rows); res->s1.resize(n_rows); res->e1.resize(n_rows); res->s2.resize(n_rows);
       res->e2.resize(n_rows); res->errs.resize(n_rows); res->cols.resize(n_rows);
-      D.d2h(res->ref.data(), c_ref, sizeof(int) * n_rows); D.d2h(res->qry.data(), c_qry, sizeof(int) * n_rows);
-      D.d2h(res->s1.data(), c_sA, sizeof(int) * n_rows); D.d2h(res->e1.data(), c_eA, sizeof(int) * n_rows);
-      D.d2h(res->s2.data(), c_sB, sizeof(int) * n_rows); D.d2h(res->e2.data(), c_eB, sizeof(int) * n_rows);
-      D.d2h(res->errs.data(), c_errs, sizeof(int) * n_rows); D.d2h(res->cols.data(), c_cols, sizeof(int) * n_rows);
+      {
+        std::vector<int> host_rows(8 * (size_t)n_rows);
+        D.d2h(host_rows.data(), c_all, sizeof(int) * 8 * (size_t)n_rows);
+        std::vector<int>* dst[8] = {&res->ref, &res->qry, &res->s1, &res->e1, &res->s2, &res->e2, &res->errs, &res->cols};
+        for (int c = 0; c < 8; c++) memcpy(dst[c]->data(), host_rows.data() + (size_t)c * n_rows, sizeof(int) * (size_t)n_rows);
+      }
       if (want_deltas) {
         unsigned long long used[2] = {0, 0};
         D.d2h(used, DO.used, sizeof(used));
