@@ -72,6 +72,9 @@ struct ExtCtx {
   mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw, acc_caps;   // per-warp statistics, flushed once per kernel
   mutable TbCtx T;
   mutable int pk_fail;           // packed engine only: a field did not fit, the read goes to the general engine
+  // The alignment the walk is working on, kept in registers (the same values on every lane): a row in HBM that lane 0 has just
+  // written is a trip to L2 for the next read of it, and the walk touches the current row several times per match.
+  mutable int c_idx, c_sA, c_sB, c_eA, c_eB, c_cols, c_errs;
   SeqView A; SeqView B[2];
   RowsOut R; int al0, al1;       // alignments of the current (record, read) group: rows [al0, al1)
   const int* ord; int nC;        // clusters of the group in walking order -> split cluster id
@@ -483,57 +486,83 @@ MFSC_DEV int c_s1(const ExtCtx& E, int c, int t) { return (int)(E.cm_s1[E.pc_fir
 MFSC_DEV int c_s2(const ExtCtx& E, int c, int t) { return E.cm_s2[E.pc_first[E.ord[c]] + t] + 1; }
 MFSC_DEV int c_len(const ExtCtx& E, int c, int t) { return E.cm_len[E.pc_first[E.ord[c]] + t]; }
 
+// the cached row goes back to HBM (all lanes hold the same values; lane 0 writes)
+MFSC_DEV void rc_flush(const ExtCtx& E) {
+  if (E.c_idx < 0) return;
+  if (E.lane == 0) {
+    const int k = E.c_idx;
+    E.R.sA[k] = E.c_sA; E.R.sB[k] = E.c_sB; E.R.eA[k] = E.c_eA; E.R.eB[k] = E.c_eB; E.R.cols[k] = E.c_cols; E.R.errs[k] = E.c_errs;
+  }
+  wsync();
+  E.c_idx = -1;
+}
+// make row ci the cached one
+MFSC_DEV void rc_bind(const ExtCtx& E, int ci) {
+  if (E.c_idx == ci) return;
+  rc_flush(E);
+  E.c_idx = ci;
+  E.c_sA = E.R.sA[ci]; E.c_sB = E.R.sB[ci]; E.c_eA = E.R.eA[ci]; E.c_eB = E.R.eB[ci]; E.c_cols = E.R.cols[ci]; E.c_errs = E.R.errs[ci];
+}
+MFSC_DEV int r_sA(const ExtCtx& E, int k) { return k == E.c_idx ? E.c_sA : E.R.sA[k]; }
+MFSC_DEV int r_sB(const ExtCtx& E, int k) { return k == E.c_idx ? E.c_sB : E.R.sB[k]; }
+MFSC_DEV int r_eA(const ExtCtx& E, int k) { return k == E.c_idx ? E.c_eA : E.R.eA[k]; }
+MFSC_DEV int r_eB(const ExtCtx& E, int k) { return k == E.c_idx ? E.c_eB : E.R.eB[k]; }
+
 template <bool TB, bool PK>
 MFSC_DEV bool ext_forward(ExtCtx& E, int ci, int tA, int tB, bool forced, bool optimal) {
-  const int eA = E.R.eA[ci], eB = E.R.eB[ci], dir = E.R.dir[ci];
+  rc_bind(E, ci);
+  const int eA = E.c_eA, eB = E.c_eB, dir = E.R.dir[ci];
   bool overflow = false;
   if (tA - eA + 1 > DP_MAX_ALN) { tA = eA + DP_MAX_ALN - 1; overflow = true; optimal = true; }
   if (tB - eB + 1 > DP_MAX_ALN) { tB = eB + DP_MAX_ALN - 1; overflow = true; optimal = true; }
   DpOut o = dp_run<TB, PK>(E, dir, eA, eB, +1, tA - eA + 1, tB - eB + 1, forced, optimal, true);
   // the DP re-aligns the alignment's last column
-  wsync();
-  if (E.lane == 0) {
-    E.R.cols[ci] += o.cols - 1; E.R.errs[ci] += o.errs;
-    E.R.eA[ci] = eA + o.fi - 1; E.R.eB[ci] = eB + o.fj - 1;
-    if (TB) { tok_drop_last_column(E, ci); tok_append(E, ci, tok_from_rev(E, o.n_ops)); }
+  E.c_cols += o.cols - 1; E.c_errs += o.errs;
+  E.c_eA = eA + o.fi - 1; E.c_eB = eB + o.fj - 1;
+  if (TB) {
+    wsync();
+    if (E.lane == 0) { tok_drop_last_column(E, ci); tok_append(E, ci, tok_from_rev(E, o.n_ops)); }
+    wsync();
   }
-  wsync();
   return o.reached && !overflow;
 }
 
 template <bool TB, bool PK>
 MFSC_DEV bool ext_backward(ExtCtx& E, int ci, int ti) {
-  const int sA = E.R.sA[ci], sB = E.R.sB[ci], dir = E.R.dir[ci];
+  rc_bind(E, ci);
+  const int sA = E.c_sA, sB = E.c_sB, dir = E.R.dir[ci];
   int tA, tB; bool optimal = false, overflow = false;
-  if (ti >= 0) { tA = E.R.eA[ti]; tB = E.R.eB[ti]; } else { tA = 1; tB = 1; optimal = true; }
+  if (ti >= 0) { tA = r_eA(E, ti); tB = r_eB(E, ti); } else { tA = 1; tB = 1; optimal = true; }
   if (sA - tA + 1 > DP_MAX_ALN) { tA = sA - DP_MAX_ALN + 1; overflow = true; optimal = true; }
   if (sB - tB + 1 > DP_MAX_ALN) { tB = sB - DP_MAX_ALN + 1; overflow = true; optimal = true; }
   DpOut o = dp_run<TB, PK>(E, dir, sA, sB, -1, sA - tA + 1, sB - tB + 1, false, optimal, false);
   bool reached = o.reached;
   if (overflow || ti < 0) reached = false;
   if (reached) {
-    ext_forward<TB, PK>(E, ti, sA, sB, true, false);
+    ext_forward<TB, PK>(E, ti, sA, sB, true, false);      // binds ti (row ci went back to HBM)
     // the target now ends on this alignment's first column; append the rest and drop this alignment
-    if (E.lane == 0) {
-      E.R.cols[ti] += E.R.cols[ci] - 1; E.R.errs[ti] += E.R.errs[ci];
-      E.R.eA[ti] = E.R.eA[ci]; E.R.eB[ti] = E.R.eB[ci];
-      if (TB) {
+    E.c_cols += E.R.cols[ci] - 1; E.c_errs += E.R.errs[ci];
+    E.c_eA = E.R.eA[ci]; E.c_eB = E.R.eB[ci];
+    if (TB) {
+      wsync();
+      if (E.lane == 0) {
         tok_drop_first_column(E, ci);
         if (E.R.tail[ti] >= 0 && E.R.head[ci] >= 0) { E.T.arena[E.R.tail[ti]] = E.R.head[ci]; E.R.tail[ti] = E.R.tail[ci]; } else E.T.bad = 1;
       }
+      wsync();
     }
-    wsync();
     E.al1--;
   } else {
     const int nsA = sA - o.fi + 1, nsB = sB - o.fj + 1;
     DpOut o2 = dp_run<TB, PK>(E, dir, nsA, nsB, +1, sA - nsA + 1, sB - nsB + 1, true, false, true);
-    wsync();
-    if (E.lane == 0) {
-      E.R.cols[ci] += o2.cols - 1; E.R.errs[ci] += o2.errs;
-      E.R.sA[ci] = nsA; E.R.sB[ci] = nsB;
-      if (TB) { tok_drop_first_column(E, ci); tok_prepend(E, ci, tok_from_rev(E, o2.n_ops)); }
+    rc_bind(E, ci);
+    E.c_cols += o2.cols - 1; E.c_errs += o2.errs;
+    E.c_sA = nsA; E.c_sB = nsB;
+    if (TB) {
+      wsync();
+      if (E.lane == 0) { tok_drop_first_column(E, ci); tok_prepend(E, ci, tok_from_rev(E, o2.n_ops)); }
+      wsync();
     }
-    wsync();
   }
   return reached;
 }
@@ -544,7 +573,7 @@ MFSC_DEV bool ext_shadowed(const ExtCtx& E, int c, int ap) {
   const int sA = c_s1(E, c, 0), eA = c_s1(E, c, nm - 1) + c_len(E, c, nm - 1) - 1;
   const int sB = c_s2(E, c, 0), eB = c_s2(E, c, nm - 1) + c_len(E, c, nm - 1) - 1;
   for (int k = ap; k >= E.al0; k--)
-    if (E.R.dir[k] == dir && E.R.eA[k] >= eA && E.R.eB[k] >= eB && E.R.sA[k] <= sA && E.R.sB[k] <= sB) return true;
+    if (E.R.dir[k] == dir && r_eA(E, k) >= eA && r_eB(E, k) >= eB && r_sA(E, k) <= sA && r_sB(E, k) <= sB) return true;
   return false;
 }
 
@@ -571,12 +600,12 @@ MFSC_DEV int ext_forward_target(const ExtCtx& E, int cur, int& tA, int& tB) {
 }
 
 MFSC_DEV int ext_reverse_target(const ExtCtx& E, int cur) {
-  const int sA = E.R.sA[cur], sB = E.R.sB[cur], dir = E.R.dir[cur];
+  const int sA = r_sA(E, cur), sB = r_sB(E, cur), dir = E.R.dir[cur];
   int dist = sA < sB ? sA : sB;
   int res = -1;
   for (int k = cur - 1; k >= E.al0; k--) {
     if (E.R.dir[k] != dir) continue;
-    const int eA = E.R.eA[k], eB = E.R.eB[k];
+    const int eA = r_eA(E, k), eB = r_eB(E, k);
     if (eA <= sA && eB <= sB) {
       int greater, lesser;
       if (sA - eA > sB - eB) { greater = sA - eA; lesser = sB - eB; } else { lesser = sA - eA; greater = sB - eB; }
@@ -603,32 +632,34 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
       }
     }
     const int nm = c_nm(E, cur), dir = c_dir(E, cur);
+    const int first = E.pc_first[E.ord[cur]];         // the cluster's matches: cm_*[first .. first + nm)
     int tl_ok = 0, tl_cols = 0, tl_errs = 0, tl_chunk = -1;          // this lane's small rectangle of the current chunk of gaps
     for (int mi = 0; mi < nm; mi++) {
-      const int ms1 = c_s1(E, cur, mi), ms2 = c_s2(E, cur, mi), mlen = c_len(E, cur, mi);
+      const int ms1 = (int)(E.cm_s1[first + mi] - E.a_ostart) + 1, ms2 = E.cm_s2[first + mi] + 1, mlen = E.cm_len[first + mi];
       if (target_reached) {
-        if (E.R.eA[curA] != ms1 || E.R.eB[curA] != ms2) continue;   // walk to the match the DP landed on
-        wsync();
-        if (E.lane == 0) {
-          E.R.eA[curA] += mlen - 1; E.R.eB[curA] += mlen - 1; E.R.cols[curA] += mlen - 1;
-          if (TB && mlen > 1) tok_append(E, curA, tok_run(E, mlen - 1));
+        rc_bind(E, curA);
+        if (E.c_eA != ms1 || E.c_eB != ms2) continue;   // walk to the match the DP landed on
+        E.c_eA += mlen - 1; E.c_eB += mlen - 1; E.c_cols += mlen - 1;
+        if (TB && mlen > 1) {
+          wsync();
+          if (E.lane == 0) tok_append(E, curA, tok_run(E, mlen - 1));
+          wsync();
         }
-        wsync();
       } else {
+        rc_flush(E);
         curA = E.al1++;
         wsync();
         if (E.lane == 0) {
           E.R.ref[curA] = E.ref_id; E.R.qry[curA] = E.qry_id; E.R.dir[curA] = dir;
-          E.R.sA[curA] = ms1; E.R.sB[curA] = ms2; E.R.eA[curA] = ms1 + mlen - 1; E.R.eB[curA] = ms2 + mlen - 1;
-          E.R.cols[curA] = mlen; E.R.errs[curA] = 0;
           if (TB) { const int c = tok_run(E, mlen); E.R.head[curA] = c; E.R.tail[curA] = c; }
         }
         wsync();
+        E.c_idx = curA; E.c_sA = ms1; E.c_sB = ms2; E.c_eA = ms1 + mlen - 1; E.c_eB = ms2 + mlen - 1; E.c_cols = mlen; E.c_errs = 0;
         const int ti = ext_reverse_target(E, curA);
         if (ext_backward<TB, PK>(E, curA, ti)) curA = ti;
       }
       if (mi < nm - 1) {
-        tA = c_s1(E, cur, mi + 1); tB = c_s2(E, cur, mi + 1);
+        tA = (int)(E.cm_s1[first + mi + 1] - E.a_ostart) + 1; tB = E.cm_s2[first + mi + 1] + 1;
         bool taken = false;
         if (PK && !TB) {
           // the gaps of this cluster, 32 at a time, one small rectangle per lane (dp_tiny_lane)
@@ -637,26 +668,26 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
             const int g = tl_chunk * MFSC_LANES + E.lane;
             tl_ok = 0;
             if (g < nm - 1) {
-              const int gA = c_s1(E, cur, g) + c_len(E, cur, g) - 1, gB = c_s2(E, cur, g) + c_len(E, cur, g) - 1;
-              const int gN = c_s1(E, cur, g + 1) - gA + 1, gM = c_s2(E, cur, g + 1) - gB + 1;
+              const int gl = E.cm_len[first + g];
+              const int gA = (int)(E.cm_s1[first + g] - E.a_ostart) + gl, gB = E.cm_s2[first + g] + gl;
+              const int gN = (int)(E.cm_s1[first + g + 1] - E.a_ostart) + 1 - gA + 1, gM = E.cm_s2[first + g + 1] + 1 - gB + 1;
               if (gN >= 1 && gM >= 1 && gN <= TL_MAX && gM <= TL_MAX && gN + gM <= pk_tiny_limit(E.P.breaklen, E.P.band_cap))
                 tl_ok = dp_tiny_lane(E, dir, gA, gB, gN, gM, &tl_cols, &tl_errs) ? 1 : 0;
             }
           }
           const int src = mi % MFSC_LANES;
           const int ok = wbcast_i32(tl_ok, src), gcols = wbcast_i32(tl_cols, src), gerrs = wbcast_i32(tl_errs, src);
-          const int eA = E.R.eA[curA], eB = E.R.eB[curA];
+          rc_bind(E, curA);
+          const int eA = E.c_eA, eB = E.c_eB;
           if (ok && !E.pk_fail && eA == ms1 + mlen - 1 && eB == ms2 + mlen - 1) {
             const int gN = tA - eA + 1, gM = tB - eB + 1;
-            wsync();
+            E.c_cols += gcols - 1; E.c_errs += gerrs;
+            E.c_eA = tA; E.c_eB = tB;
             if (E.lane == 0) {
-              E.R.cols[curA] += gcols - 1; E.R.errs[curA] += gerrs;
-              E.R.eA[curA] = tA; E.R.eB[curA] = tB;
               E.acc_cells += (unsigned long long)(gN + 1) * (unsigned long long)(gM + 1) - 1ull; E.acc_calls += 1ull;
               const int mw = (gN < gM ? gN : gM) + 1;
               if (mw > E.acc_maxw) E.acc_maxw = mw;
             }
-            wsync();
             target_reached = true;
             taken = true;
           }
@@ -673,6 +704,7 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
     wsync();
     if (!target_reached) cur = ++prev; else cur = targetC;
   }
+  rc_flush(E);
 }
 
 struct ExtIn {
@@ -765,6 +797,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0; E.acc_caps = 0;
     E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.cap = 0; E.T.top = 0; E.T.bad = 0;
     E.pk_fail = 0;
+    E.c_idx = -1; E.c_sA = E.c_sB = E.c_eA = E.c_eB = E.c_cols = E.c_errs = 0;
     if (TB) {
       const long long wg = warp_global();
       E.T.tb = pool.tb + (size_t)wg * TB_DIAGS * DP_SLOTS;
