@@ -89,6 +89,7 @@ static inline void st_volatile_u64(volatile unsigned long long* p, unsigned long
 static inline void dev_threadfence() {}
 template <class T> static inline T ldg(const T* p) { return *p; }
 template <class T> static inline T ld_stream(const T* p) { return *p; }
+template <class T> static inline void st_stream(T* p, T v) { *p = v; }
 
 #else
 // ------------------------------------------------------------------------------------------
@@ -153,6 +154,7 @@ MFSC_DEV void dev_threadfence() { __threadfence(); }
 template <class T> MFSC_DEV T ldg(const T* p) { return __ldg(p); }
 // streaming load: evict-first in L2, so a one-touch random stream does not displace the reused tables
 template <class T> MFSC_DEV T ld_stream(const T* p) { return __ldcs(p); }
+template <class T> MFSC_DEV void st_stream(T* p, T v) { __stcs(p, v); }
 #endif
 
 // common helpers --------------------------------------------------------------------------

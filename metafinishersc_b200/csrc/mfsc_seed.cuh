@@ -143,11 +143,11 @@ MFSC_DEV void seed_emit(const SeedCtx& C, unsigned r, int p, int left, int right
   const unsigned long long slot = mem_slot(C.out.counter);
   if (slot < C.out.capacity) {
     const int rec = seq_of(C.R.start, C.R.n_seq, s1p);
-    C.out.qs[slot] = C.qs;
-    C.out.s1[slot] = s1p - C.R.start[rec] + C.r_ostart[rec];
-    C.out.s2[slot] = s2;
-    C.out.len[slot] = total;
-    C.out.rec[slot] = rec;
+    st_stream(&C.out.qs[slot], C.qs);
+    st_stream(&C.out.s1[slot], s1p - C.R.start[rec] + C.r_ostart[rec]);
+    st_stream(&C.out.s2[slot], s2);
+    st_stream(&C.out.len[slot], total);
+    st_stream(&C.out.rec[slot], rec);
   }
 }
 
@@ -226,8 +226,10 @@ MFSC_KERNEL k_seeds(SeqStore R, const unsigned* r_ostart, KmerIndex X, SeqStore 
           const unsigned wa = w0 + (unsigned)x < wmax ? w0 + (unsigned)x : wmax, wb = w0 + (unsigned)x + 1u < wmax ? w0 + (unsigned)x + 1u : wmax;
 #if !defined(MFSC_EMU)
           if (wb == wa + 1u && (wa & 1u) == 0u) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(Q.txt + wa);
-            const uint2 iv = *reinterpret_cast<const uint2*>(Q.inv + wa);
+            // the reads stream through once: evict-first, so that they do not push the index (directory, heads, positions,
+            // reference text -- re-read by every probe) out of L2
+            const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(Q.txt + wa));
+            const uint2 iv = __ldcs(reinterpret_cast<const uint2*>(Q.inv + wa));
             S.txt[x] = v.x; S.txt[x + 1] = v.y; S.inv[x] = iv.x; S.inv[x + 1] = iv.y;
           } else
 #endif
