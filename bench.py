@@ -269,8 +269,8 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
                 "list": [torch.zeros((cap, 8), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None}
 
     n_local = len(off) - 1
-    # pieces of about 300 Mbp: a piece costs about a millisecond of fixed work (launches, syncs, sort set-up), so small shards go up whole
-    n_pieces = max(1, min(args.strong_pieces, n_local, int(round(float(off[-1]) / 300e6))))
+    # pieces of about 100 Mbp (a piece costs about a millisecond of fixed work: launches, syncs, sort set-up), at most --strong-pieces
+    n_pieces = max(1, min(args.strong_pieces, n_local, int(round(float(off[-1]) / 100e6))))
     cuts = [n_local * k // n_pieces for k in range(n_pieces + 1)]
 
     def one_step():

@@ -827,7 +827,17 @@ int mfsc_index_build_sharded(mfsc_comm* c, const uint8_t* bases, const int64_t* 
   mfsc_index* ix = new mfsc_index();
   ix->device = D.device;
   std::string err;
-  if (!seq_upload(D, bases, rec_off, n_rec, 0, true, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
+  const int N = c->world, me = c->rank;
+  // the contigs cross PCIe once: rank 0 uploads and packs them, the packed text (0.375 B per base) goes to the other ranks over
+  // NVLink -- eight ranks uploading the same 50 MB next to their read batches compete for the host's memory bandwidth
+  if (!seq_upload(D, bases, rec_off, n_rec, 0, me == 0, ix->ref, err)) { index_release(D, ix); return fail(MFSC_ERR_NOMEM, err); }
+  {
+    int nrc0 = g_nccl.GroupStart();
+    if (!nrc0) nrc0 = g_nccl.Broadcast(ix->ref.txt, ix->ref.txt, sizeof(unsigned long long) * (size_t)ix->ref.n_words, NCCL_U8, 0, c->comms[0], c->streams[0]);
+    if (!nrc0) nrc0 = g_nccl.Broadcast(ix->ref.inv, ix->ref.inv, sizeof(unsigned) * (size_t)ix->ref.n_words, NCCL_U8, 0, c->comms[0], c->streams[0]);
+    { int e2 = g_nccl.GroupEnd(); if (!nrc0) nrc0 = e2; }
+    if (nrc0) { index_release(D, ix); return fail(MFSC_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(nrc0)); }
+  }
   ix->h_ostart.resize(n_rec);
   for (int r = 0; r < n_rec; r++) ix->h_ostart[r] = (unsigned)(rec_off[r] - rec_off[0] + r);
   ix->ostart = dalloc<unsigned>(D, n_rec);
@@ -835,7 +845,6 @@ int mfsc_index_build_sharded(mfsc_comm* c, const uint8_t* bases, const int64_t* 
   D.h2d(ix->ostart, ix->h_ostart.data(), sizeof(unsigned) * n_rec);
   ix->k = choose_k(p, ix->ref.n_bases);
   ix->n_buckets = 1ll << (2 * ix->k);
-  const int N = c->world, me = c->rank;
   const long long words = ix->n_buckets / 32;
   auto word_lo = [&](int r) { return words * r / N; };
   if (ms) ms[0] = since(t0);
