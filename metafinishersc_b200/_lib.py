@@ -12,7 +12,17 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MFSC_LIB_DEV") or os.path.join(_HERE, "csrc", "libmfsc_b200.so")   # MFSC_LIB_DEV: developer hook to A/B another build of the same CUDA library
+LIB_PATH = os.path.join(_HERE, "csrc", "libmfsc_b200.so")
+_DEV = os.environ.get("MFSC_LIB_DEV")        # developer hook: A/B another nvcc build of the SAME CUDA library (tools/, build_ab/)
+if _DEV:
+    _real = os.path.realpath(_DEV)
+    _root = os.path.dirname(_HERE)
+    for _bad in (os.path.join(_root, "oracle"), os.path.join(_root, "tests")):
+        if _real.startswith(os.path.realpath(_bad) + os.sep):
+            raise ImportError("MFSC_LIB_DEV must name a CUDA build of libmfsc_b200, not test infrastructure (%s)" % _real)
+    if "emu" in os.path.basename(_real) or "oracle" in os.path.basename(_real):
+        raise ImportError("MFSC_LIB_DEV must name a CUDA build of libmfsc_b200, not test infrastructure (%s)" % _real)
+    LIB_PATH = _real
 
 c_i32, c_i64, c_vp, c_dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_double
 
