@@ -271,6 +271,8 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
     n_local = len(off) - 1
     # pieces of about 100 Mbp (a piece costs about a millisecond of fixed work: launches, syncs, sort set-up), at most --strong-pieces
     n_pieces = max(1, min(args.strong_pieces, n_local, int(round(float(off[-1]) / 100e6))))
+    if args.strong_pieces_exact:
+        n_pieces = max(1, min(args.strong_pieces_exact, n_local))
     cuts = [n_local * k // n_pieces for k in range(n_pieces + 1)]
 
     def one_step():
@@ -375,13 +377,15 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
         w, last = one_step()
         walls.append(w)
     wall = sum(walls)
-    t = torch.tensor([wall, last["align_ms"], -last["align_ms"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, last["align_ms"], -last["align_ms"]] + walls, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall_max, align_max, align_min = float(t[0].item()), float(t[1].item()), -float(t[2].item())
+    walls_max = [float(x) for x in t[3:].tolist()]
     return {"workload": "cfg3 as one job: 10 chimeric contigs x %d bp, %d reads x 10 kbp (%.0f Mbp), 1%% del + 1%% ins, contiguous read "
                         "batches over %d rank(s)" % (G, n_total, bases_total / 1e6, world),
             "scaling": "strong", "value": bases_total * K / (wall_max * 1e-3) / 1e6, "unit": "Mbp/s", "steps": K, "ms_per_step": wall_max / K,
+            "step_walls_ms_max_over_ranks": [round(x, 2) for x in walls_max],
             "index": ("sharded build: every rank packs the contigs and builds 1/N of the k-mer space, slices exchanged with grouped NCCL broadcasts"
                       if world > 1 and args.strong_index == "sharded" else "built on rank 0, NCCL broadcast of the 5 index buffers") if world > 1 else "built in place",
             "pieces_per_rank": n_pieces,
@@ -449,8 +453,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="cfg2 is the headline; the others are BASELINE's other shapes")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: the sharded cfg3 job becomes the primary line")
     ap.add_argument("--no-strong", action="store_true", help="skip the sharded cfg3 job")
+    ap.add_argument("--strong-only", action="store_true", help="only the sharded cfg3 job (experiments)")
     ap.add_argument("--no-wrapper", action="store_true", help="skip the file-level alignerRobot.largeRvsQAlign measurement")
-    ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--strong-steps", type=int, default=6)
+    ap.add_argument("--strong-pieces-exact", type=int, default=0, help="force the number of pieces (experiments)")
     ap.add_argument("--strong-pieces", type=int, default=4, help="sub-batches a rank's reads go up in (upload of piece k+1 overlaps the alignment of piece k)")
     ap.add_argument("--strong-index", default="sharded", choices=["sharded", "broadcast"],
                     help="N > 1: every rank builds 1/N of the index and the slices are exchanged (sharded), or rank 0 builds and broadcasts")
@@ -478,6 +484,18 @@ def main():
             dist.broadcast(t, src=src)
             buf[:] = t.cpu().numpy()
         comm = multigpu.RankComm(E, rank, world, exchange)
+    if args.strong_only:
+        strong = measure_strong(E, args, rank, world, local, comm, torch, dist)
+        if rank == 0:
+            emit(json.dumps({"metric": METRIC, "value": strong["value"], "unit": "Mbp/s", "n_gpus": world, "steps": strong["steps"], "warmup": args.warmup,
+                             "ms_per_step": strong["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+                             "data": "synthetic", "config": {"workload": strong["workload"]}, "strong": strong}))
+        if comm is not None:
+            comm.free()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     P = engine.make_params(engine=args.engine, kmer=args.kmer)
     contigs, reads, label = make_workload(rank, args)
     buf, off = engine._as_buf(reads)
