@@ -599,6 +599,7 @@ def main():
     resident.free()
     del flush
     torch.cuda.empty_cache()
+    E.trim_pool()            # the sharded job starts from an empty scratch pool, as it would in a process of its own
     strong = None
     if not args.no_strong:
         strong = measure_strong(E, args, rank, world, local, comm, torch, dist)

@@ -58,6 +58,9 @@ int mfsc_set_device(int32_t device);
 /* The library keeps one stream per calling thread (created by the thread's first call).  A worker thread that is about to
  * end releases it with this call; the next call of the thread would create a new one. */
 int mfsc_thread_release(void);
+/* Scratch of finished calls stays in the device's stream-ordered memory pool for the next call (no release threshold).  This
+ * gives it back to the driver: between two phases of very different batch sizes, or before handing the GPU to someone else. */
+int mfsc_trim_pool(void);
 void mfsc_default_params(mfsc_params* p);
 
 /* pinned host memory for the buffers handed to the calls below (optional, speeds up the copies) */

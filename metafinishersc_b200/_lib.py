@@ -49,7 +49,7 @@ KEEP_MEMS, KEEP_CLUSTERS, STOP_SEEDS, STOP_CLUSTERS, WANT_DELTAS = 1, 2, 4, 8, 1
  RF_END_SPAN, RF_OVERLAP) = [1 << i for i in range(11)]
 
 # every symbol include/mfsc.h declares (tests check the library exports all of them)
-SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_device", "mfsc_thread_release", "mfsc_default_params",
+SYMBOLS = ["mfsc_last_error", "mfsc_version", "mfsc_device_count", "mfsc_set_device", "mfsc_thread_release", "mfsc_trim_pool", "mfsc_default_params",
            "mfsc_host_alloc", "mfsc_host_free", "mfsc_index_build", "mfsc_index_create", "mfsc_index_info",
            "mfsc_index_buffers", "mfsc_index_build_ms", "mfsc_index_free", "mfsc_comm_unique_id", "mfsc_comm_init_rank",
            "mfsc_comm_init_local", "mfsc_index_broadcast", "mfsc_comm_free", "mfsc_index_build_sharded", "mfsc_reads_upload", "mfsc_reads_free",

@@ -369,6 +369,18 @@ int mfsc_thread_release(void) {
   return MFSC_OK;
 }
 
+int mfsc_trim_pool(void) {
+#ifndef MFSC_EMU
+  Dev& D = g_dev;
+  if (!D.ok()) return fail(MFSC_ERR_CUDA, "no CUDA device");
+  cudaDeviceSynchronize();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, D.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  cudaGetLastError();
+#endif
+  return MFSC_OK;
+}
+
 void mfsc_default_params(mfsc_params* p) {
   memset(p, 0, sizeof(*p));
   p->minmatch = 20; p->mincluster = 65; p->maxgap = 90; p->breaklen = 200; p->diagdiff = 5; p->maxmatch = 1; p->simplify = 1;

@@ -132,6 +132,10 @@ class Engine:
     def set_device(self, d):
         check(self.L, self.L.mfsc_set_device(d))
 
+    def trim_pool(self):
+        """Gives the scratch kept in the device's memory pool back to the driver (mfsc_trim_pool)."""
+        check(self.L, self.L.mfsc_trim_pool())
+
     def thread_release(self):
         """Destroys the calling thread's stream (worker threads call it before they end)."""
         self.L.mfsc_thread_release()
