@@ -385,7 +385,7 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
     return {"workload": "cfg3 as one job: 10 chimeric contigs x %d bp, %d reads x 10 kbp (%.0f Mbp), 1%% del + 1%% ins, contiguous read "
                         "batches over %d rank(s)" % (G, n_total, bases_total / 1e6, world),
             "scaling": "strong", "value": bases_total * K / (wall_max * 1e-3) / 1e6, "unit": "Mbp/s", "steps": K, "ms_per_step": wall_max / K,
-            "step_walls_ms_max_over_ranks": [round(x, 2) for x in walls_max],
+            "step_walls_ms_max_over_ranks": [round(x, 2) for x in walls_max], "ms_per_step_median": statistics.median(walls_max),
             "index": ("sharded build: every rank packs the contigs and builds 1/N of the k-mer space, slices exchanged with grouped NCCL broadcasts"
                       if world > 1 and args.strong_index == "sharded" else "built on rank 0, NCCL broadcast of the 5 index buffers") if world > 1 else "built in place",
             "pieces_per_rank": n_pieces,
