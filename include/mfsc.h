@@ -71,11 +71,9 @@ int mfsc_host_free(void* p);
  * rec_off[n_rec+1]: offsets of the records in bases. */
 int mfsc_index_build(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                      mfsc_index** out);
-/* Replication over several GPUs: the root rank builds the index; every other rank creates an empty one of the
- * same shape (`build_tables` = 0, `p->kmer` and `n_positions` taken from the root's mfsc_index_info, `bases` may be
- * NULL), then all ranks fetch the device buffers with mfsc_index_buffers and broadcast them (NCCL through
- * torch.distributed, one call per buffer).  info: [0] k, [1] device, [2] text words, [3] occupied buckets, [4] positions,
- * [5] bytes in HBM, [6] records, [7] bases. */
+/* mfsc_index_build with its round-1 signature: build_tables must be 1 (empty shells for a broadcast through other means are no
+ * longer made here -- replicas come from mfsc_index_broadcast / mfsc_index_build_sharded below); n_positions is ignored.
+ * mfsc_index_info: [0] k, [1] device, [2] text words, [3] occupied buckets, [4] positions, [5] bytes in HBM, [6] records, [7] bases. */
 int mfsc_index_create(const uint8_t* bases, const int64_t* rec_off, int32_t n_rec, const mfsc_params* p,
                       int32_t build_tables, int64_t n_positions, mfsc_index** out);
 int mfsc_index_info(const mfsc_index* ix, int64_t info[8]);

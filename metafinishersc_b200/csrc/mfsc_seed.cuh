@@ -19,8 +19,6 @@ struct DevParams {
   int pk_clean, pk_prio, pk_score;   // PK_CLEAN, PK_P, PK_SCORE, opaque to the compiler like `one`
 };
 
-struct ProbeChunk { int qs, pb, pe; };
-
 struct MemOut {
   int* qs; unsigned* s1; int* s2; int* len; int* rec;
   unsigned long long* counter;   // matches found (64-bit: it keeps counting past the capacity, the host then retries with a larger buffer)

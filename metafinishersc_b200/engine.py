@@ -141,12 +141,11 @@ class Engine:
         self.L.mfsc_thread_release()
 
     # -- stage 1 ---------------------------------------------------------------------------
-    def index(self, contigs, params=None, build_tables=True, n_positions=0):
+    def index(self, contigs, params=None):
         params = params or make_params()
         buf, off = _as_buf(contigs)
         h = ctypes.c_void_p()
-        check(self.L, self.L.mfsc_index_create(ptr(buf) if build_tables else None, ptr(off), len(off) - 1,
-                                               ctypes.byref(params), int(build_tables), n_positions, ctypes.byref(h)))
+        check(self.L, self.L.mfsc_index_build(ptr(buf), ptr(off), len(off) - 1, ctypes.byref(params), ctypes.byref(h)))
         return Index(self.L, h, len(off) - 1)
 
     # -- stages 2-4 ------------------------------------------------------------------------
