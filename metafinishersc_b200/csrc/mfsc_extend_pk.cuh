@@ -314,18 +314,26 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
   unsigned cells = 0;                              // at most 2 * DP_MAX_ALN diagonals of < 256 cells
   int maxw = 0;
   int d;
-  for (d = 1; d <= N + M && (d - FinD) <= breaklen && nlo <= nhi; d++) {
+  // the walk ends after anti-diagonal dEnd = min(N + M, FinD + breaklen): kept up to date where FinD changes, so the loop tests one
+  // limit; the two window-refill tests are one countdown (the window fronts move by at most one position per anti-diagonal)
+  int dEnd = N + M < breaklen ? N + M : breaklen;
+  int safe = (fillA - (1 - nlo)) < (fillB - nhi) ? (fillA - (1 - nlo)) : (fillB - nhi);
+  for (d = 1; d <= dEnd && nlo <= nhi; d++) {
     const int w = nhi - nlo + 1;
     cells += (unsigned)w;
     if (w > maxw) maxw = w;
-    if (d - nlo > fillA) {
-      if (wmax_i32(pk_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
-      fillA += DP_FILL; wsync();
+    if (safe < 0) {
+      if (d - nlo > fillA) {
+        if (wmax_i32(pk_fill(RS, Av, a0, dirn, N, fillA, 0, wA, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
+        fillA += DP_FILL; wsync();
+      }
+      if (nhi > fillB) {
+        if (wmax_i32(pk_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
+        fillB += DP_FILL; wsync();
+      }
+      safe = (fillA - (d - nlo)) < (fillB - nhi) ? (fillA - (d - nlo)) : (fillB - nhi);
     }
-    if (nhi > fillB) {
-      if (wmax_i32(pk_fill(QS, Bv, b0, dirn, M, fillB, 1, wB, lane) ? 1 : 0)) { E.pk_fail = 1; return o; }
-      fillB += DP_FILL; wsync();
-    }
+    safe--;
     int* cB = bBase + (d & 1) * DP_SLOTS;
     int lkey = -0x7fffffff;
     const int glo = nlo >> 2, ghi = nhi >> 2;
@@ -355,20 +363,23 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
       }
     }
 #endif
-    const int dkey = wmax_i32(lkey);
-    const int dmaxF = dkey >> PK_SB;
-    const int dj = nlo + (dkey & 0xff);
-    const bool upd = forced || dmaxF >= highF;
-    highF = upd ? dmaxF : highF; FinD = upd ? d : FinD;
-    // lanes 0..3 write the halo, lane 4 records the finish cell: one predicated store each, no branch.
+    // A new best needs a cell at or above the best so far.  Most anti-diagonals have none (the best path advances two
+    // anti-diagonals per matching pair, and noisy reads spend long stretches below their best): one vote decides, and the
+    // maximum reduction, the finish-cell record and the updates run only when something can change.
+    if (forced || wballot((lkey >> PK_SB) >= highF) != 0u) {
+      const int dkey = wmax_i32(lkey);
+      const int dj = nlo + (dkey & 0xff);
+      highF = dkey >> PK_SB; FinD = d;
+      dEnd = d + breaklen < N + M ? d + breaklen : N + M;
+      const int dW = cB[dj & DP_SMASK];
+      if (lane == (MFSC_LANES == 1 ? 0 : 4)) st4(rec, dj, dW, accU, accM);
+    }
+    // lanes 0..3 write the halo: one predicated store each, no branch.
     // halo: the next diagonal reads nD[nlo-1 .. nhi] and nI[nlo .. nhi+1]; diagonal d+2 reads best[nlo-1 .. nhi+1]
     {
-      const int dW = cB[dj & DP_SMASK];
 #if MFSC_LANES == 1
-      if (upd) st4(rec, dj, dW, accU, accM);
       nD[(nlo - 1) & DP_SMASK] = PK_SENT; nI[(nhi + 1) & DP_SMASK] = PK_SENT; cB[(nlo - 1) & DP_SMASK] = PK_SENT; cB[(nhi + 1) & DP_SMASK] = PK_SENT;
 #else
-      if (upd && lane == 4) st4(rec, dj, dW, accU, accM);
       int* hp = halo_base + (d & 1) * halo_par + ((nlo - 1 + halo_hi * (w + 1)) & DP_SMASK);
       if (lane < 4) *hp = PK_SENT;
 #endif
