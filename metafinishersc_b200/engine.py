@@ -200,8 +200,12 @@ class Engine:
         check(self.L, self.L.mfsc_align_reads(index.h, reads.h, ctypes.byref(params), flags, ctypes.byref(h)))
         return self._collect(h, flags)
 
-    def align(self, index, reads, params=None, flags=0):
-        """Host buffers in, rows out: what one `nucmer` + `show-coords` job produced."""
+    PIECE_BASES = 96_000_000      # Engine.align pipelines batches of at least two pieces of this size
+
+    def align(self, index, reads, params=None, flags=0, pieces=None):
+        """Host buffers in, rows out: what one `nucmer` + `show-coords` job produced.  A large batch goes up in pieces on a
+        second host thread / stream, so that the upload (and packing) of piece k+1 overlaps the alignment of piece k; every
+        read is aligned on its own, so the rows are those of one call.  pieces: None = by size, 1 = one call."""
         params = params or make_params()
         buf, off = _as_buf(reads)
         if len(off) <= 1:
@@ -211,9 +215,81 @@ class Engine:
             r.stats, r.ms, r.mems, r.clusters = {}, {}, None, None
             r.delta_begin = r.delta_end = r.deltas = None
             return r
-        h = ctypes.c_void_p()
-        check(self.L, self.L.mfsc_align_batch(index.h, ptr(buf), ptr(off), len(off) - 1, ctypes.byref(params), flags, ctypes.byref(h)))
-        return self._collect(h, flags)
+        n = len(off) - 1
+        if pieces is None:
+            pieces = min(4, int((off[-1] - off[0]) // self.PIECE_BASES))
+        if flags & (KEEP_MEMS | KEEP_CLUSTERS | STOP_SEEDS | STOP_CLUSTERS):
+            pieces = 1
+        pieces = max(1, min(pieces, n))
+        if pieces <= 1:
+            h = ctypes.c_void_p()
+            check(self.L, self.L.mfsc_align_batch(index.h, ptr(buf), ptr(off), n, ctypes.byref(params), flags, ctypes.byref(h)))
+            return self._collect(h, flags)
+        return self._align_pipelined(index, buf, off, params, flags, pieces)
+
+    def _align_pipelined(self, index, buf, off, params, flags, pieces):
+        import queue
+        import threading
+        n = len(off) - 1
+        # cut by bases, at read boundaries
+        targets = off[0] + (off[-1] - off[0]) * np.arange(1, pieces) // pieces
+        cuts = [0] + [int(x) for x in np.searchsorted(off, targets)] + [n]
+        cuts = sorted(set(cuts))
+        q = queue.Queue()
+        dev = index.info()["device"]
+
+        def up():
+            E2 = None
+            try:
+                E2 = Engine(self.L)
+                E2.set_device(dev)
+                for k in range(len(cuts) - 1):
+                    lo, hi = cuts[k], cuts[k + 1]
+                    q.put(E2.upload((buf[off[lo] - off[0]:off[hi] - off[0]], off[lo:hi + 1] - off[lo])))
+            except Exception as e:        # surfaced in the caller's thread
+                q.put(e)
+            finally:
+                if E2 is not None:
+                    E2.thread_release()
+        th = threading.Thread(target=up)
+        th.start()
+        parts = []
+        try:
+            for k in range(len(cuts) - 1):
+                rd = q.get()
+                if isinstance(rd, Exception):
+                    raise rd
+                try:
+                    parts.append(self.align_reads(index, rd, params, flags))
+                finally:
+                    rd.free()
+        finally:
+            th.join()
+            while not q.empty():
+                x = q.get()
+                if isinstance(x, Reads):
+                    x.free()
+        r = Rows()
+        for f in ("ref_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            setattr(r, f, np.concatenate([getattr(p, f) for p in parts]))
+        r.qry_id = np.concatenate([p.qry_id + cuts[k] for k, p in enumerate(parts)])
+        r.stats = {}
+        for key in parts[0].stats:
+            vals = [p.stats[key] for p in parts]
+            r.stats[key] = max(vals) if key == "max_band" else sum(vals)
+        r.stats["h2d_bytes"] = int(off[-1] - off[0]) + 8 * (n + 1) + 28 * n
+        r.stats["launches"] += len(parts)
+        r.ms = {key: sum(p.ms[key] for p in parts) for key in parts[0].ms}
+        r.mems = r.clusters = None
+        r.delta_begin = r.delta_end = r.deltas = None
+        if flags & WANT_DELTAS:
+            base, db, de, dl = 0, [], [], []
+            for p in parts:
+                ok = p.delta_begin >= 0
+                db.append(np.where(ok, p.delta_begin + base, -1)); de.append(np.where(ok, p.delta_end + base, -1)); dl.append(p.deltas)
+                base += len(p.deltas)
+            r.delta_begin, r.delta_end, r.deltas = np.concatenate(db), np.concatenate(de), np.concatenate(dl)
+        return r
 
     # -- stage 5 ---------------------------------------------------------------------------
     def coverage(self, ref_id, s1, e1, contig_off, want_ms=False):

@@ -354,3 +354,24 @@ def test_write_double_and_reverse_complement(tmp_path):
         want = "".join("%s%d_p\n%s\n%s%d_d\n%s\n" % (hdr, i, s, hdr, i, rc_ref(s)) for i, s in enumerate(seqs))
         assert open(folder + "out.fasta").read() == want
     assert IORobot.reverseComplement("ACGTNacgtnX") == rc_ref("ACGTNacgtnX")
+
+
+def test_pipelined_align_equals_one_call(emu_engine):
+    """Engine.align splits a large batch into pieces (upload of piece k+1 on a second host thread while piece k is aligned):
+    the rows, the delta lists and the statistics are those of one call."""
+    from metafinishersc_b200 import engine
+    d = datagen.abun_gap(G=40_000, repeat_len=900, L=2500, seed=11)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = [r.translate(comp)[::-1] if i % 2 else r for i, r in enumerate(d["reads"][:50])] + [b"", b"ACGT"]
+    P = engine.make_params()
+    ix = emu_engine.index(d["contigs"], P)
+    for flags in (0, engine.WANT_DELTAS):
+        one = emu_engine.align(ix, reads, P, flags=flags, pieces=1)
+        many = emu_engine.align(ix, reads, P, flags=flags, pieces=4)
+        for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            assert np.array_equal(getattr(one, f), getattr(many, f)), f
+        assert one.stats["cells"] == many.stats["cells"] and one.stats["max_band"] == many.stats["max_band"] and len(one) > 40
+        if flags:
+            for i in range(len(one)):
+                assert np.array_equal(one.deltas[one.delta_begin[i]:one.delta_end[i]], many.deltas[many.delta_begin[i]:many.delta_end[i]])
+    ix.free()
