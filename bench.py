@@ -7,7 +7,7 @@ resident in HBM.
 Primary line (`value`, every N): BASELINE.json configs[1] -- one 5 Mbp genome, 50X of 10 kbp reads with 15 % indel error
 (25 000 reads, ~250 Mbp) PER GPU: reads shard by batch with no data-path collective, so the contract's `"scaling": "weak"`.
   value       : Mbp/s with the read batch already packed in HBM (CUDA events inside the library around the step)
-  e2e         : the same metric through mfsc_align_batch from pinned HOST buffers, timed with the HOST clock around the
+  e2e         : the same metric through Engine.align (mfsc_align_batch; pieces via mfsc_reads_upload + mfsc_align_reads for a large batch) from pinned HOST buffers, timed with the HOST clock around the
                 call a user makes (H2D of the reads, D2H of the rows, ctypes marshalling all inside)
   e2e_wrapper : the same reads as FASTA files through the reference-facing alignerRobot.largeRvsQAlign (split into 20
                 parts, 20 nucmer jobs, .delta and coords files written, rows returned), N = 1 only

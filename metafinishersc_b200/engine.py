@@ -200,12 +200,18 @@ class Engine:
         check(self.L, self.L.mfsc_align_reads(index.h, reads.h, ctypes.byref(params), flags, ctypes.byref(h)))
         return self._collect(h, flags)
 
-    PIECE_BASES = 96_000_000      # Engine.align pipelines batches of at least two pieces of this size
+    # Engine.align pipelines a batch of at least two pieces of PIECE_BASES when the copy is a large share of the call.  Every piece
+    # ends with the tail of its slowest reads (one warp per read), so pieces pay only where reads are cheap: measured, accurate 6 kbp
+    # reads (27 Gbp/s on the device) 21.6 -> 20.1 ms in four pieces, 10 kbp reads at 15 % error (2 Gbp/s) 130 -> 137 ms in two.
+    # The rate of the previous call on the same index decides; a first call goes up whole.
+    PIECE_BASES = 96_000_000
+    PIECE_MIN_RATE = 8e9          # bases per second of device time
 
     def align(self, index, reads, params=None, flags=0, pieces=None):
         """Host buffers in, rows out: what one `nucmer` + `show-coords` job produced.  A large batch goes up in pieces on a
         second host thread / stream, so that the upload (and packing) of piece k+1 overlaps the alignment of piece k; every
-        read is aligned on its own, so the rows are those of one call.  pieces: None = by size, 1 = one call."""
+        read is aligned on its own, so the rows are those of one call.  pieces: None = by size and the device rate of the previous
+        call on this index, 1 = one call."""
         params = params or make_params()
         buf, off = _as_buf(reads)
         if len(off) <= 1:
@@ -217,15 +223,22 @@ class Engine:
             return r
         n = len(off) - 1
         if pieces is None:
-            pieces = min(4, int((off[-1] - off[0]) // self.PIECE_BASES))
+            bases = int(off[-1] - off[0])
+            pieces = min(4, bases // self.PIECE_BASES) if getattr(index, "_rate", 0.0) >= self.PIECE_MIN_RATE else 1
         if flags & (KEEP_MEMS | KEEP_CLUSTERS | STOP_SEEDS | STOP_CLUSTERS):
             pieces = 1
         pieces = max(1, min(pieces, n))
         if pieces <= 1:
             h = ctypes.c_void_p()
             check(self.L, self.L.mfsc_align_batch(index.h, ptr(buf), ptr(off), n, ctypes.byref(params), flags, ctypes.byref(h)))
-            return self._collect(h, flags)
-        return self._align_pipelined(index, buf, off, params, flags, pieces)
+            r = self._collect(h, flags)
+        else:
+            r = self._align_pipelined(index, buf, off, params, flags, pieces)
+        if flags == 0 or flags == WANT_DELTAS:
+            dev_s = (r.ms.get("total", 0.0) - r.ms.get("upload", 0.0)) * 1e-3
+            if dev_s > 0:
+                index._rate = float(off[-1] - off[0]) / dev_s
+        return r
 
     def _align_pipelined(self, index, buf, off, params, flags, pieces):
         import queue

@@ -374,4 +374,15 @@ def test_pipelined_align_equals_one_call(emu_engine):
         if flags:
             for i in range(len(one)):
                 assert np.array_equal(one.deltas[one.delta_begin[i]:one.delta_end[i]], many.deltas[many.delta_begin[i]:many.delta_end[i]])
+    # pieces=None: the first call on an index goes up whole, later ones in pieces when the device rate of the previous call was high
+    assert getattr(ix, "_rate", 0) > 0
+    old = engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE
+    try:
+        engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE = 20_000, 0.0
+        auto = emu_engine.align(ix, reads, P)
+        assert auto.stats["launches"] > one.stats["launches"] and np.array_equal(auto.s1, one.s1) and np.array_equal(auto.qry_id, one.qry_id)
+        engine.Engine.PIECE_MIN_RATE = 1e30
+        assert emu_engine.align(ix, reads, P).stats["launches"] == one.stats["launches"]
+    finally:
+        engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE = old
     ix.free()
