@@ -42,7 +42,10 @@ typedef struct mfsc_params {
   double diagfactor;   /* -d  0.12 */
   int32_t kmer;        /* index k-mer length, 0 = choose from the reference size */
   int32_t engine;      /* stage-4 DP engine: 0 = packed 32-bit states first, reads whose fields do not fit are extended
-                          again by the general engine (same rows either way); 1 = general engine only */
+                          again by the general engine (same rows either way); 1 = general engine only.  With the packed
+                          engine the forward extensions that do not depend on the walk run as independent tasks ahead
+                          of it (stage 4a) when the cluster matches cover at least half of the reads' bases; 2 = packed,
+                          stage 4a always; 3 = packed, never.  The rows are the same in every mode */
   int32_t pk_u_span;   /* packed engine: widest spread of the gap-column / mismatch counters over a band that a */
   int32_t pk_m_span;   /* rebase accepts; 0 = the field capacity.  Smaller values only force more reads to engine 1 */
 } mfsc_params;
@@ -146,7 +149,8 @@ int mfsc_result_clusters(const mfsc_result* r, int32_t* qry_id, int32_t* strand,
 int mfsc_result_deltas(const mfsc_result* r, int64_t* begin, int64_t* end, int32_t* deltas);
 /* stats[16]: 0 DP cells, 1 DP calls, 2 widest band, 3 probes, 4 matches, 5 kernel launches,
  * 6 algorithmic bytes of the seed kernel, 7 h2d bytes, 8 d2h bytes, 9 reads handed from the packed to the general DP engine,
- * 10 anti-diagonals on which band_cap trimmed the band (0: the cap never bound, the rows are those of an uncapped DP);
+ * 10 anti-diagonals on which band_cap trimmed the band (0: the cap never bound, the rows are those of an uncapped DP),
+ * 11 gaps between cluster matches aligned as independent tasks ahead of the walk, 12 how many of those results the walk used;
  * ms[16]: 0 upload+pack, 1 seeds, 2 sort, 3 cluster, 4 extend, 5 compact+download, 6 total */
 int mfsc_result_stats(const mfsc_result* r, int64_t stats[16], double ms[16]);
 int mfsc_result_free(mfsc_result* r);

@@ -41,7 +41,7 @@
 
 struct DpOut { int reached, fi, fj, cols, errs, n_ops; };
 
-struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max_band; unsigned long long* caps; };   // caps: anti-diagonals on which band_cap trimmed the band
+struct ExtStats { unsigned long long* cells; unsigned long long* calls; int* max_band; unsigned long long* caps; unsigned long long* gaps; };   // caps: anti-diagonals on which band_cap trimmed the band
 
 // View of one sequence: 1-based position i lives at padded position base + i - 1
 struct SeqView { unsigned base; int n; };
@@ -69,7 +69,7 @@ struct DeltaOut { int* buf; unsigned long long* used; long long cap; unsigned* n
 
 struct ExtCtx {
   SeqStore RS, QS; DevParams P; int* sm; ExtStats st;
-  mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw, acc_caps;   // per-warp statistics, flushed once per kernel
+  mutable unsigned long long acc_cells, acc_calls; mutable int acc_maxw, acc_caps, acc_gaps;   // per-warp statistics, flushed once per kernel
   mutable TbCtx T;
   mutable int pk_fail;           // packed engine only: a field did not fit, the read goes to the general engine
   // The alignment the walk is working on, kept in registers (the same values on every lane): a row in HBM that lane 0 has just
@@ -83,6 +83,7 @@ struct ExtCtx {
   const unsigned* cm_s1; const int* cm_s2; const int* cm_len;
   unsigned a_ostart;             // separator-joined coordinate of A's first base
   int ref_id, qry_id, lane;
+  const int4* gap_res;           // stage 4a results per cluster match (mfsc_gaps.cuh), or nullptr
 };
 
 // Best of three states with the tie rule of the reference DP: D only when strictly above both,
@@ -616,6 +617,40 @@ MFSC_DEV int ext_reverse_target(const ExtCtx& E, int cur) {
   return res;
 }
 
+// Gaps between consecutive matches of a cluster that stage 4a (mfsc_gaps.cuh) aligns as independent tasks
+#define GAP_MIN 32                    // one of the sides longer than this
+MFSC_DEV bool gap_is_task(int gN, int gM) {
+  return gN >= 1 && gM >= 1 && (gN > GAP_MIN || gM > GAP_MIN) && gN <= DP_MAX_ALN && gM <= DP_MAX_ALN;
+}
+// A stage 4a result, as stored per start match: x = 1 | reached << 1 | fi << 2 | fj << 17, y = columns | errors << 16,
+// z = cells | widest band << 23, w = the target it was computed for (gap_target_key).
+MFSC_DEV int gap_target_key(int tA, int tB) { return tA * 31 + tB; }
+// Stage 4a pays where the walk between its tasks is light: accurate reads, whose cluster matches cover most of their bases
+// (measured: reads vs reads at 1 % error -12 % on stage 4, reads vs contigs at 1 % -2..5 %).  On reads at 15 % error the
+// alignments break and restart often, the backward searches and forced re-alignments that follow stay in the walk and
+// are as long as the tasks, and the split costs 2 %: there the walk does everything, as without stage 4a.  The plan
+// kernel sums the matched bases; every consumer applies this test to the same two numbers.
+MFSC_DEV bool gap_stage_on(unsigned long long matched, long long qbases) { return 2ull * matched >= (unsigned long long)qbases; }
+// The walk stands on row ci and is about to extend forward from (sA, sB) = the end of cluster match m towards (tA, tB):
+// if stage 4a has run exactly that DP, its outcome is applied to the row.  Returns 0 (nothing taken), 1 (taken, target
+// not reached) or 2 (taken, target reached).
+MFSC_DEV int gap_take(ExtCtx& E, int ci, int m, int sA, int sB, int tA, int tB) {
+  if (E.gap_res == nullptr || E.pk_fail) return 0;
+  rc_bind(E, ci);
+  if (E.c_eA != sA || E.c_eB != sB) return 0;
+  const int4 r = E.gap_res[m];
+  if (!(r.x & 1) || r.w != gap_target_key(tA, tB)) return 0;
+  const int fi = (r.x >> 2) & 0x7fff, fj = (r.x >> 17) & 0x7fff;
+  E.c_cols += (r.y & 0xffff) - 1; E.c_errs += (r.y >> 16) & 0xffff;
+  E.c_eA = sA + fi - 1; E.c_eB = sB + fj - 1;
+  if (E.lane == 0) {
+    E.acc_cells += (unsigned long long)(r.z & 0x7fffff); E.acc_calls += 1ull; E.acc_gaps += 1;
+    const int mw = (r.z >> 23) & 0xff;
+    if (mw > E.acc_maxw) E.acc_maxw = mw;
+  }
+  return (r.x & 2) ? 2 : 1;
+}
+
 // Walk the clusters of one (record, read) group in order; returns nothing, alignments are rows [al0, al1)
 template <bool TB, bool PK>
 MFSC_DEV void ext_clusters(ExtCtx& E) {
@@ -692,11 +727,18 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
             taken = true;
           }
         }
+        if (PK && !TB && !taken && gap_is_task(tA - (ms1 + mlen - 1) + 1, tB - (ms2 + mlen - 1) + 1)) {
+          const int got = gap_take(E, curA, first + mi, ms1 + mlen - 1, ms2 + mlen - 1, tA, tB);
+          if (got) { target_reached = got > 1; taken = true; }
+        }
         if (!taken) target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, false);
       } else {
         tA = E.A.n; tB = E.B[0].n;
         targetC = ext_forward_target(E, cur, tA, tB);
-        target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, targetC < 0);
+        int got = 0;
+        if (PK && !TB) got = gap_take(E, curA, first + mi, ms1 + mlen - 1, ms2 + mlen - 1, tA, tB);
+        if (got) target_reached = got > 1;
+        else target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, targetC < 0);
       }
     }
     if (targetC < 0) target_reached = false;
@@ -717,7 +759,55 @@ struct ExtIn {
   // reads to extend: all of them (list == nullptr) or list[0 .. *n_list).  The packed-engine instantiation appends the
   // reads it has to hand over to the general engine to retry[0 .. *n_retry).
   const int* list; const unsigned* n_list; int* retry; unsigned* n_retry;
+  const int4* gap_res;                  // stage 4a results (mfsc_gaps.cuh) for the walk to pick up, or nullptr
+  int ord_ready;                        // stage 4a has already written the walking order (ext_order) of every read
+  const unsigned long long* gap_matched; long long gap_qbases;     // stage 4a's switch, see gap_stage_on
 };
+
+// Walking order of the clusters of one read (both strands), into I.ord[b0 .. b0 + n0 + n1): reference records in order of first
+// appearance in the cluster stream (the order of the delta file's `>ref qry` blocks), then start in the record, strand,
+// start in the read, emission order.  Also clears the clusters' `fused` flags.
+MFSC_DEV void ext_order(const ExtIn& I, int b0, int b1, int n0, int n1, int lane) {
+  const int nC = n0 + n1;
+  int* ord = I.ord + b0;
+  int* tmp = I.key_tmp + b0;
+  // split cluster ids of the read: forward strand b0..b0+n0, reverse strand b1..b1+n1.
+  // Walking order: reference records in order of first appearance in that stream (the order of the
+  // delta file's `>ref qry` blocks), then start in the record, strand, start in the read, emission order.
+  for (int x = lane; x < nC; x += MFSC_LANES) {
+    const int pc = x < n0 ? b0 + x : b1 + (x - n0);
+    tmp[x] = pc;
+    I.fused[pc] = 0;
+  }
+  wsync();
+  for (int x = lane; x < nC; x += MFSC_LANES) {
+    const int rec = I.pc_rec[tmp[x]];
+    int f = x;
+    for (int y = 0; y < x; y++) if (I.pc_rec[tmp[y]] == rec) { f = y; break; }
+    I.grp[b0 + x] = f;
+  }
+  wsync();
+  for (int x = lane; x < nC; x += MFSC_LANES) {
+    const int pc = tmp[x];
+    const int grp = I.grp[b0 + x]; const unsigned s1 = I.cm_s1[I.pc_first[pc]]; const int dir = pc >= b1 ? 1 : 0;
+    const int s2 = I.cm_s2[I.pc_first[pc]];
+    int rank = 0;
+    for (int y = 0; y < nC; y++) {
+      const int pd = tmp[y];
+      const int grp2 = I.grp[b0 + y]; const unsigned t1 = I.cm_s1[I.pc_first[pd]]; const int dir2 = pd >= b1 ? 1 : 0;
+      const int t2 = I.cm_s2[I.pc_first[pd]];
+      bool before;
+      if (grp2 != grp) before = grp2 < grp;
+      else if (t1 != s1) before = t1 < s1;
+      else if (dir2 != dir) before = dir2 < dir;
+      else if (t2 != s2) before = t2 < s2;
+      else before = y < x;
+      rank += before ? 1 : 0;
+    }
+    ord[rank] = pc;
+  }
+  wsync();
+}
 
 #ifdef MFSC_EMU
 static thread_local int emu_dp_smem[DP_SMEM_INTS];
@@ -727,7 +817,7 @@ static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #define MFSC_EXT_MINBLOCKS 6
 #endif
 #ifndef MFSC_EXT_MINBLOCKS_PK
-#define MFSC_EXT_MINBLOCKS_PK 8
+#define MFSC_EXT_MINBLOCKS_PK 7
 #endif
 struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; int arena_ints; };
 
@@ -741,7 +831,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * (PK ? PK_SMEM_INTS : DP_SMEM_INTS);
 #endif
   const int lane = lane_id();
-  unsigned long long w_cells = 0, w_calls = 0, w_caps = 0; int w_maxw = 0;
+  unsigned long long w_cells = 0, w_calls = 0, w_caps = 0, w_gaps = 0; int w_maxw = 0;
   const int n_work = I.list ? (int)*I.n_list : n_reads;
   // reads are handed out by a ticket counter: a warp takes the next read when it is done with its own
   for (;;) {
@@ -755,46 +845,10 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     const int nC = n0 + n1;
     if (nC == 0) { if (lane == 0) R.n_rows[q] = 0; continue; }
     int* ord = I.ord + b0;
-    int* tmp = I.key_tmp + b0;
-    // split cluster ids of the read: forward strand b0..b0+n0, reverse strand b1..b1+n1.
-    // Walking order: reference records in order of first appearance in that stream (the order of the
-    // delta file's `>ref qry` blocks), then start in the record, strand, start in the read, emission order.
-    for (int x = lane; x < nC; x += MFSC_LANES) {
-      const int pc = x < n0 ? b0 + x : b1 + (x - n0);
-      tmp[x] = pc;
-      I.fused[pc] = 0;
-    }
-    wsync();
-    for (int x = lane; x < nC; x += MFSC_LANES) {
-      const int rec = I.pc_rec[tmp[x]];
-      int f = x;
-      for (int y = 0; y < x; y++) if (I.pc_rec[tmp[y]] == rec) { f = y; break; }
-      I.grp[b0 + x] = f;
-    }
-    wsync();
-    for (int x = lane; x < nC; x += MFSC_LANES) {
-      const int pc = tmp[x];
-      const int grp = I.grp[b0 + x]; const unsigned s1 = I.cm_s1[I.pc_first[pc]]; const int dir = pc >= b1 ? 1 : 0;
-      const int s2 = I.cm_s2[I.pc_first[pc]];
-      int rank = 0;
-      for (int y = 0; y < nC; y++) {
-        const int pd = tmp[y];
-        const int grp2 = I.grp[b0 + y]; const unsigned t1 = I.cm_s1[I.pc_first[pd]]; const int dir2 = pd >= b1 ? 1 : 0;
-        const int t2 = I.cm_s2[I.pc_first[pd]];
-        bool before;
-        if (grp2 != grp) before = grp2 < grp;
-        else if (t1 != s1) before = t1 < s1;
-        else if (dir2 != dir) before = dir2 < dir;
-        else if (t2 != s2) before = t2 < s2;
-        else before = y < x;
-        rank += before ? 1 : 0;
-      }
-      ord[rank] = pc;
-    }
-    wsync();
+    if (!I.ord_ready) ext_order(I, b0, b1, n0, n1, lane);
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
-    E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0; E.acc_caps = 0;
+    E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0; E.acc_caps = 0; E.acc_gaps = 0;
     E.T.tb = nullptr; E.T.rev = nullptr; E.T.arena = nullptr; E.T.cap = 0; E.T.top = 0; E.T.bad = 0;
     E.pk_fail = 0;
     E.c_idx = -1; E.c_sA = E.c_sB = E.c_eA = E.c_eB = E.c_cols = E.c_errs = 0;
@@ -807,6 +861,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     E.B[0].base = QS.start[2 * q]; E.B[0].n = QS.len[2 * q];
     E.B[1].base = QS.start[2 * q + 1]; E.B[1].n = QS.len[2 * q + 1];
     E.pc_rc0 = b1; E.pc_first = I.pc_first; E.pc_n = I.pc_n; E.fused = I.fused;
+    E.gap_res = (I.gap_res != nullptr && gap_stage_on(*I.gap_matched, I.gap_qbases)) ? I.gap_res : nullptr;
     E.cm_s1 = I.cm_s1; E.cm_s2 = I.cm_s2; E.cm_len = I.cm_len;
     E.qry_id = (int)q;
     int row0 = b0, rows = 0;
@@ -848,13 +903,15 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
       }
       wsync();
     }
-    w_cells += E.acc_cells; w_calls += E.acc_calls; w_caps += (unsigned long long)E.acc_caps; if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
+    w_cells += E.acc_cells; w_calls += E.acc_calls; w_caps += (unsigned long long)E.acc_caps; w_gaps += (unsigned long long)E.acc_gaps;
+    if (E.acc_maxw > w_maxw) w_maxw = E.acc_maxw;
   }
   if (lane == 0 && w_calls) {
     atomic_add_u64(st.cells, w_cells);
     atomic_add_u64(st.calls, w_calls);
     atomic_max_i32(st.max_band, w_maxw);
     if (w_caps) atomic_add_u64(st.caps, w_caps);
+    if (w_gaps) atomic_add_u64(st.gaps, w_gaps);
   }
 }
 

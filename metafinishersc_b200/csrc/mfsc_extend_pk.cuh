@@ -41,6 +41,17 @@
 
 MFSC_DEV int pk_max(int a, int b) { return a > b ? a : b; }
 
+// Ordering of the band arrays inside one anti-diagonal.  The lanes of a warp run this loop converged: every branch in it is on a
+// warp-uniform condition, per-lane differences are predicated stores, and each anti-diagonal passes a warp vote.  A converged warp
+// issues its shared-memory instructions in program order for all lanes, so between the loads and the stores of a pass the compiler
+// must be kept from reordering, but no warp barrier has to be issued (__syncwarp costs three issue slots here, five times per
+// anti-diagonal: the divergence test, its mask and the barrier).  -DMFSC_PK_HARDSYNC=1 restores the barriers.
+#if defined(MFSC_EMU) || MFSC_PK_HARDSYNC
+#define PK_ORDER() wsync()
+#else
+#define PK_ORDER() asm volatile("" ::: "memory")
+#endif
+
 // dp_fill that also reports whether this lane decoded a base of the sequence proper that is not ACGT
 MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_local, int from, int off, unsigned char* win, int lane) {
   const int to = from + DP_FILL < n_local + 8 ? from + DP_FILL : n_local + 8;
@@ -91,7 +102,7 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     const unsigned bw = wB32[(j0 >> 2) & (DP_WIN / 4 - 1)];                                                              \
     const unsigned awr = dev_byte_rev(aw);                                                                               \
     const unsigned xm = awr ^ bw;               /* per byte (= cell): non-zero where the two bases differ */             \
-    wsync();                                                                                                             \
+    PK_ORDER();                                                                                                             \
     int o0b, o0d, o0i, o1b, o1d, o1i, o2b, o2d, o2i, o3b, o3d, o3i;                                                      \
     unsigned o0t = 0, o1t = 0, o2t = 0, o3t = 0;                                                                         \
     PK_CELL(3, vD.z, vI.w, vB.z, o3b, o3d, o3i, o3t)                                                                     \
@@ -111,7 +122,7 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     const int kl_ = pk_max(pk_max(pk_max((o3b & kscore) | 3, (o2b & kscore) | 2), (o1b & kscore) | 1), o0b & kscore);    \
     lkey = pk_max(lkey, kl_ + r0);                                                                                       \
     B0 = o0b; B1 = o1b; B2 = o2b; B3 = o3b; BJ = j0;                                                                     \
-    wsync();                                                                                                             \
+    PK_ORDER();                                                                                                             \
   }
 
 // One pass of one cell per lane over the CNT cells below and including TOP (CNT <= 32, the lowest one is nlo).
@@ -123,7 +134,7 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     const int sD = nD[y1], sI = nI[y], sB = cB[y1];                                                                      \
     const unsigned ca1 = wA[(d - j1 - 1) & DP_WMASK], cb1 = wB[j1 & DP_WMASK];                                           \
     const unsigned xm = ca1 ^ cb1;                                                                                       \
-    wsync();                                                                                                             \
+    PK_ORDER();                                                                                                             \
     int ob, od, oi; unsigned ot = 0;                                                                                     \
     PK_CELL(0, sD, sI, sB, ob, od, oi, ot)                                                                               \
     if (act1) {                                                                                                          \
@@ -132,7 +143,7 @@ MFSC_DEV bool pk_fill(const SeqStore& S, SeqView V, int s0, int dirn, int n_loca
     }                                                                                                                    \
     lkey = pk_max(lkey, (ob & kscore) + (j1 - nlo));                                                                     \
     B0 = ob; BJ = j1;                                                                                                    \
-    wsync();                                                                                                             \
+    PK_ORDER();                                                                                                             \
   }
 
 // ------------------------------------------------------------------------------------------
@@ -428,7 +439,7 @@ MFSC_NOINLINE DpOut dp_engine_pk(const ExtCtx& E, int dir, int a0, int b0, int d
     }
 #endif
     lo = wmin_i32(lo); hi = wmax_i32(hi);
-    wsync();
+    PK_ORDER();
     const bool none = lo > hi;
     if (!none && hi - lo + 2 > band_cap) {
       int l2 = lo, h2 = hi;

@@ -36,7 +36,10 @@ extern thread_local emu_dim3 emu_threadIdx, emu_blockIdx, emu_blockDim, emu_grid
 #define gridDim emu_gridDim
 typedef int cudaStream_t;
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
+static inline int2 make_int2(int x, int y) { int2 v; v.x = x; v.y = y; return v; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 #define MFSC_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                        \

@@ -167,7 +167,8 @@ class Engine:
             ms = np.zeros(16, dtype=np.float64)
             check(L, L.mfsc_result_stats(h, ptr(st), ptr(ms)))
             r.stats = dict(cells=int(st[0]), dp_calls=int(st[1]), max_band=int(st[2]), probes=int(st[3]), mems=int(st[4]),
-                           launches=int(st[5]), seed_bytes=int(st[6]), h2d_bytes=int(st[7]), d2h_bytes=int(st[8]), dp_retry_reads=int(st[9]), cap_hits=int(st[10]))
+                           launches=int(st[5]), seed_bytes=int(st[6]), h2d_bytes=int(st[7]), d2h_bytes=int(st[8]), dp_retry_reads=int(st[9]), cap_hits=int(st[10]),
+                           gap_tasks=int(st[11]), gap_hits=int(st[12]))
             r.ms = dict(upload=ms[0], seeds=ms[1], sort=ms[2], cluster=ms[3], extend=ms[4], download=ms[5], total=ms[6])
             r.mems = r.clusters = None
             r.delta_begin = r.delta_end = r.deltas = None

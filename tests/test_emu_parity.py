@@ -14,6 +14,11 @@ def test_emu_matches_oracle(case, emu_engine, oracle):
     name, ref, qry, opts = case
     bad, r, o = cases.run_case(emu_engine, oracle, ref, qry, opts)
     assert not bad, "%s: %s" % (name, "; ".join(bad))
+    # stage 4a (mfsc_gaps.cuh): on where the cluster matches cover the reads (accurate reads), off on noisy ones unless forced
+    if name in ("reads_vs_contigs", "both_strands", "gap_stage_forced_noisy"):
+        assert r.stats["gap_tasks"] > 50 and 0 < r.stats["gap_hits"] <= r.stats["gap_tasks"]
+    if name in ("indel15_reads", "gap_stage_off_accurate"):
+        assert r.stats["gap_hits"] == 0
 
 
 def test_emu_coverage(emu_engine, oracle):

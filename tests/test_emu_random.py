@@ -53,6 +53,7 @@ def scenario(seed):
                 band_cap=int(rng.choice([24, 64, 248])), maxmatch=bool(rng.random() < 0.7), simplify=bool(rng.random() < 0.8))
     if rng.random() < 0.3:
         opts["pk_m_span"] = int(rng.integers(1, 20))     # push some reads through the hand-over path
+    opts["engine"] = int(rng.choice([0, 2, 2, 3]))       # stage 4a by rule / forced / off (same rows in every mode)
     return contigs, reads, opts
 
 

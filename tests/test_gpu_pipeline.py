@@ -89,14 +89,16 @@ def test_engines_agree_on_substitution_errors(gpu_engine):
         a[m] = acgt[rng.integers(0, 4, size=int(m.sum()))]
         reads.append(a.tobytes())
     out = []
-    for eng in (0, 1):
+    for eng in (0, 1, 2, 3):        # packed (stage 4a by rule), general, packed with stage 4a forced / off
         P = engine.make_params(engine=eng)
         ix = gpu_engine.index(d["contigs"], P)
         out.append(gpu_engine.align(ix, reads, P))
         ix.free()
-    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
-        assert np.array_equal(getattr(out[0], f), getattr(out[1], f)), f
-    assert out[0].stats["cells"] == out[1].stats["cells"]
+    for o in out[1:]:
+        for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+            assert np.array_equal(getattr(out[0], f), getattr(o, f)), f
+        assert out[0].stats["cells"] == o.stats["cells"] and out[0].stats["max_band"] == o.stats["max_band"]
+    assert out[2].stats["gap_hits"] > 0 and out[3].stats["gap_hits"] == 0
     assert out[0].stats["dp_retry_reads"] == 0 and len(out[0]) >= 1400
 
 

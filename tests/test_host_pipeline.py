@@ -376,6 +376,7 @@ def test_pipelined_align_equals_one_call(emu_engine):
                 assert np.array_equal(one.deltas[one.delta_begin[i]:one.delta_end[i]], many.deltas[many.delta_begin[i]:many.delta_end[i]])
     # pieces=None: the first call on an index goes up whole, later ones in pieces when the device rate of the previous call was high
     assert getattr(ix, "_rate", 0) > 0
+    one = emu_engine.align(ix, reads, P, pieces=1)
     old = engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE
     try:
         engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE = 20_000, 0.0
