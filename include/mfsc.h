@@ -44,8 +44,8 @@ typedef struct mfsc_params {
   int32_t engine;      /* stage-4 DP engine: 0 = packed 32-bit states first, reads whose fields do not fit are extended
                           again by the general engine (same rows either way); 1 = general engine only.  With the packed
                           engine the forward extensions that do not depend on the walk run as independent tasks ahead
-                          of it (stage 4a) when the cluster matches cover at least half of the reads' bases; 2 = packed,
-                          stage 4a always; 3 = packed, never.  The rows are the same in every mode */
+                          of it (stage 4a) when the batch has at least 1000 matches per read (reads against reads,
+                          repeats); 2 = packed, stage 4a always; 3 = packed, never.  The rows are the same in every mode */
   int32_t pk_u_span;   /* packed engine: widest spread of the gap-column / mismatch counters over a band that a */
   int32_t pk_m_span;   /* rebase accepts; 0 = the field capacity.  Smaller values only force more reads to engine 1 */
 } mfsc_params;

@@ -1158,7 +1158,7 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
       I.seg = seg; I.n_pc = o_npc; I.pc_first = o_pcf; I.pc_n = o_pcn; I.pc_rec = o_pcr; I.cm_s1 = o_s1; I.cm_s2 = o_s2; I.cm_len = o_len;
       I.r_ostart = ix->ostart; I.ord = x_ord; I.key_tmp = x_tmp; I.grp = x_grp; I.fused = x_fused;
       I.list = nullptr; I.n_list = nullptr; I.retry = x_retry; I.n_retry = (unsigned*)(d_stats + 4);
-      I.gap_res = nullptr; I.ord_ready = 0; I.gap_matched = nullptr; I.gap_qbases = 0;
+      I.gap_res = nullptr; I.ord_ready = 0;
       ExtStats st; st.cells = d_stats; st.calls = d_stats + 1; st.max_band = (int*)(d_stats + 2); st.caps = d_stats + 5; st.gaps = d_stats + 7;
       const int ext_block = 128;
       const size_t ext_smem = (size_t)(ext_block / MFSC_LANES) * DP_SMEM_INTS * sizeof(int);
@@ -1184,15 +1184,16 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
         if (p->engine == 1) {
           MFSC_LAUNCH((k_extend<false, false>), ext_grid, ext_block, ext_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
         } else {
-          // stage 4a: the gaps between consecutive matches of a cluster as independent tasks (mfsc_gaps.cuh)
+          // stage 4a (mfsc_gaps.cuh): the forward extensions that do not depend on the walk, as independent tasks ahead of it.
+          // It pays where the work per read is large and uneven -- reads against reads, repeats: thousands of matches per read,
+          // measured -12 % on stage 4 -- and costs a few per cent where a read is one or two alignments (the walk kernel that
+          // can pick results up is the slower instantiation), so the match count per read decides; engine 2 / 3 force it on / off.
           static const bool gap_env = getenv("MFSC_NO_GAP_TASKS") == nullptr;
-          const bool gap_tasks = gap_env && p->engine != 3;
-          const long long gap_qbases = p->engine == 2 ? 0 : rd->q.n_bases;      // engine 2: stage 4a whatever the reads look like
+          const bool gap_tasks = gap_env && p->engine != 3 && (p->engine == 2 || M >= (long long)MFSC_GAP_MIN_MATCHES_PER_READ * n_reads);
+          const unsigned pk_grid = resident_grid((const void*)k_extend<false, true>, pk_smem, 7);
           if (gap_tasks) {
-            DA(int4, g_res, M); DA(int4, g_task, M); DA(int, g_rec, M); DA(unsigned long long, g_matched, 1);
-            D.zero(g_matched, sizeof(unsigned long long));
+            DA(int4, g_res, M); DA(int4, g_task, M); DA(int, g_rec, M);
             GapPlan G; G.res = g_res; G.task = g_task; G.task_rec = g_rec; G.n_task = (unsigned*)(d_stats + 6);
-            G.matched = g_matched; G.qbases = gap_qbases;
             MFSC_LAUNCH(k_gap_plan, grid_for(D, (long long)n_reads * MFSC_LANES, 128, 16), 128, 0, D.stream, RS, QS, I, n_reads, P, G);
             // (the task count is only known on the device: as many blocks as are resident, whatever the number of reads)
             unsigned gap_grid = resident_grid((const void*)k_gaps<true>, pk_smem, 7);
@@ -1205,11 +1206,13 @@ int mfsc_align_reads(mfsc_index* ix, mfsc_reads* rd, const mfsc_params* p, int32
 #endif
             MFSC_LAUNCH((k_gaps<true>), gap_grid, ext_block, pk_smem, D.stream, RS, QS, I, P, G, G.n_task + 1);
             D.launches += 2;
-            I.gap_res = g_res; I.ord_ready = 1; I.gap_matched = g_matched; I.gap_qbases = gap_qbases;
+            I.gap_res = g_res; I.ord_ready = 1;
+            const unsigned pkg_grid = resident_grid((const void*)k_extend<false, true, true>, pk_smem, 7);
+            MFSC_LAUNCH((k_extend<false, true, true>), pkg_grid, ext_block, pk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
+          } else {
+            // packed engine over every read, then the general engine over the reads it handed back (usually none)
+            MFSC_LAUNCH((k_extend<false, true>), pk_grid, ext_block, pk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
           }
-          // packed engine over every read, then the general engine over the reads it handed back (usually none)
-          const unsigned pk_grid = resident_grid((const void*)k_extend<false, true>, pk_smem, 7);
-          MFSC_LAUNCH((k_extend<false, true>), pk_grid, ext_block, pk_smem, D.stream, RS, QS, I, n_reads, P, R0, st, ext_ticket, pool, DO);
           D.launches++;
           ExtIn I2 = I;
           I2.gap_res = nullptr; I2.ord_ready = 0;

@@ -625,12 +625,6 @@ MFSC_DEV bool gap_is_task(int gN, int gM) {
 // A stage 4a result, as stored per start match: x = 1 | reached << 1 | fi << 2 | fj << 17, y = columns | errors << 16,
 // z = cells | widest band << 23, w = the target it was computed for (gap_target_key).
 MFSC_DEV int gap_target_key(int tA, int tB) { return tA * 31 + tB; }
-// Stage 4a pays where the walk between its tasks is light: accurate reads, whose cluster matches cover most of their bases
-// (measured: reads vs reads at 1 % error -12 % on stage 4, reads vs contigs at 1 % -2..5 %).  On reads at 15 % error the
-// alignments break and restart often, the backward searches and forced re-alignments that follow stay in the walk and
-// are as long as the tasks, and the split costs 2 %: there the walk does everything, as without stage 4a.  The plan
-// kernel sums the matched bases; every consumer applies this test to the same two numbers.
-MFSC_DEV bool gap_stage_on(unsigned long long matched, long long qbases) { return 2ull * matched >= (unsigned long long)qbases; }
 // The walk stands on row ci and is about to extend forward from (sA, sB) = the end of cluster match m towards (tA, tB):
 // if stage 4a has run exactly that DP, its outcome is applied to the row.  Returns 0 (nothing taken), 1 (taken, target
 // not reached) or 2 (taken, target reached).
@@ -652,7 +646,7 @@ MFSC_DEV int gap_take(ExtCtx& E, int ci, int m, int sA, int sB, int tA, int tB) 
 }
 
 // Walk the clusters of one (record, read) group in order; returns nothing, alignments are rows [al0, al1)
-template <bool TB, bool PK>
+template <bool TB, bool PK, bool GAPS>
 MFSC_DEV void ext_clusters(ExtCtx& E) {
   bool target_reached = false;
   int tA = 0, tB = 0;
@@ -727,7 +721,7 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
             taken = true;
           }
         }
-        if (PK && !TB && !taken && gap_is_task(tA - (ms1 + mlen - 1) + 1, tB - (ms2 + mlen - 1) + 1)) {
+        if (GAPS && PK && !TB && !taken && gap_is_task(tA - (ms1 + mlen - 1) + 1, tB - (ms2 + mlen - 1) + 1)) {
           const int got = gap_take(E, curA, first + mi, ms1 + mlen - 1, ms2 + mlen - 1, tA, tB);
           if (got) { target_reached = got > 1; taken = true; }
         }
@@ -736,7 +730,7 @@ MFSC_DEV void ext_clusters(ExtCtx& E) {
         tA = E.A.n; tB = E.B[0].n;
         targetC = ext_forward_target(E, cur, tA, tB);
         int got = 0;
-        if (PK && !TB) got = gap_take(E, curA, first + mi, ms1 + mlen - 1, ms2 + mlen - 1, tA, tB);
+        if (GAPS && PK && !TB) got = gap_take(E, curA, first + mi, ms1 + mlen - 1, ms2 + mlen - 1, tA, tB);
         if (got) target_reached = got > 1;
         else target_reached = ext_forward<TB, PK>(E, curA, tA, tB, false, targetC < 0);
       }
@@ -761,7 +755,6 @@ struct ExtIn {
   const int* list; const unsigned* n_list; int* retry; unsigned* n_retry;
   const int4* gap_res;                  // stage 4a results (mfsc_gaps.cuh) for the walk to pick up, or nullptr
   int ord_ready;                        // stage 4a has already written the walking order (ext_order) of every read
-  const unsigned long long* gap_matched; long long gap_qbases;     // stage 4a's switch, see gap_stage_on
 };
 
 // Walking order of the clusters of one read (both strands), into I.ord[b0 .. b0 + n0 + n1): reference records in order of first
@@ -821,7 +814,7 @@ static thread_local int emu_dp_smem[DP_SMEM_INTS];
 #endif
 struct TbPool { unsigned char* tb; unsigned char* rev; int* arena; int arena_ints; };
 
-template <bool TB, bool PK>
+template <bool TB, bool PK, bool GAPS = false>
 MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, RowsOut R, ExtStats st,
                                                    unsigned* ticket, TbPool pool, DeltaOut DO) {
 #ifdef MFSC_EMU
@@ -845,7 +838,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     const int nC = n0 + n1;
     if (nC == 0) { if (lane == 0) R.n_rows[q] = 0; continue; }
     int* ord = I.ord + b0;
-    if (!I.ord_ready) ext_order(I, b0, b1, n0, n1, lane);
+    if (!GAPS || !I.ord_ready) ext_order(I, b0, b1, n0, n1, lane);
     ExtCtx E;
     E.RS = RS; E.QS = QS; E.P = P; E.sm = sm; E.st = st; E.R = R; E.lane = lane;
     E.acc_cells = 0; E.acc_calls = 0; E.acc_maxw = 0; E.acc_caps = 0; E.acc_gaps = 0;
@@ -861,7 +854,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     E.B[0].base = QS.start[2 * q]; E.B[0].n = QS.len[2 * q];
     E.B[1].base = QS.start[2 * q + 1]; E.B[1].n = QS.len[2 * q + 1];
     E.pc_rc0 = b1; E.pc_first = I.pc_first; E.pc_n = I.pc_n; E.fused = I.fused;
-    E.gap_res = (I.gap_res != nullptr && gap_stage_on(*I.gap_matched, I.gap_qbases)) ? I.gap_res : nullptr;
+    E.gap_res = GAPS ? I.gap_res : nullptr;
     E.cm_s1 = I.cm_s1; E.cm_s2 = I.cm_s2; E.cm_len = I.cm_len;
     E.qry_id = (int)q;
     int row0 = b0, rows = 0;
@@ -873,7 +866,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
       E.ord = ord + g0; E.nC = g1 - g0;
       E.A.base = RS.start[rec]; E.A.n = RS.len[rec]; E.a_ostart = I.r_ostart[rec]; E.ref_id = rec;
       E.al0 = row0 + rows; E.al1 = E.al0;
-      ext_clusters<TB, PK>(E);
+      ext_clusters<TB, PK, GAPS>(E);
       rows = E.al1 - row0;
       g0 = g1;
     }
@@ -911,7 +904,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_extend(Se
     atomic_add_u64(st.calls, w_calls);
     atomic_max_i32(st.max_band, w_maxw);
     if (w_caps) atomic_add_u64(st.caps, w_caps);
-    if (w_gaps) atomic_add_u64(st.gaps, w_gaps);
+    if (GAPS && w_gaps) atomic_add_u64(st.gaps, w_gaps);
   }
 }
 

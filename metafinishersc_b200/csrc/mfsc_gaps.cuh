@@ -17,13 +17,15 @@
 // same arguments); cells, calls and widest band are carried along so that the statistics are the same too.
 #pragma once
 
+#ifndef MFSC_GAP_MIN_MATCHES_PER_READ
+#define MFSC_GAP_MIN_MATCHES_PER_READ 1000   // stage 4a runs when a batch has at least this many matches per read (mfsc_api.cu)
+#endif
+
 struct GapPlan {
   int4* task;                         // (start match m, strand index 2 q + dir, tA, tB; tB negated: `optimal` extension)
   int* task_rec;                      // reference record of the task
   unsigned* n_task;
   int4* res;                          // per start match, see gap_take (mfsc_extend.cuh)
-  unsigned long long* matched;        // bases in cluster matches, summed by the plan kernel (gap_stage_on)
-  long long qbases;                   // bases of the reads
 };
 
 MFSC_DEV void gap_emit(const GapPlan& G, int m, int qs, int rec, int tA, int tB, bool optimal) {
@@ -37,7 +39,6 @@ MFSC_DEV void gap_emit(const GapPlan& G, int m, int qs, int rec, int tA, int tB,
 // kind B extensions.
 MFSC_KERNEL k_gap_plan(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams P, GapPlan G) {
   const int lane = lane_id();
-  long long matched = 0;
   for (long long q = warp_global(); q < n_reads; q += warps_total()) {
     const int b0 = I.seg[2 * q], b1 = I.seg[2 * q + 1];
     const int n0 = I.n_pc[2 * q], n1 = I.n_pc[2 * q + 1];
@@ -59,7 +60,6 @@ MFSC_KERNEL k_gap_plan(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams
         const int pc = E.ord[cur], first = I.pc_first[pc], nm = I.pc_n[pc], qs = 2 * (int)q + (pc >= b1 ? 1 : 0);
         for (int t = 0; t + 1 < nm; t++) {
           const int m = first + t, gl = I.cm_len[m];
-          matched += gl;
           const int sA = (int)(I.cm_s1[m] - E.a_ostart) + gl, sB = I.cm_s2[m] + gl;
           const int tA = (int)(I.cm_s1[m + 1] - E.a_ostart) + 1, tB = I.cm_s2[m + 1] + 1;
           if (gap_is_task(tA - sA + 1, tB - sB + 1)) gap_emit(G, m, qs, rec, tA, tB, false);
@@ -67,14 +67,11 @@ MFSC_KERNEL k_gap_plan(SeqStore RS, SeqStore QS, ExtIn I, int n_reads, DevParams
         int tA = E.A.n, tB = E.B[0].n;
         const int targetC = ext_forward_target(E, cur, tA, tB);
         gap_emit(G, first + nm - 1, qs, rec, tA, tB, targetC < 0);
-        matched += I.cm_len[first + nm - 1];
       }
       g0 = g1;
     }
     wsync();
   }
-  matched = wsum_i64(matched);
-  if (lane == 0 && matched) atomic_add_u64(G.matched, (unsigned long long)matched);
 }
 
 template <bool PK>
@@ -86,7 +83,7 @@ MFSC_KERNEL_LB(128, PK ? MFSC_EXT_MINBLOCKS_PK : MFSC_EXT_MINBLOCKS) k_gaps(SeqS
   int* sm = reinterpret_cast<int*>(dp_smem4) + warp_in_block() * (PK ? PK_SMEM_INTS : DP_SMEM_INTS);
 #endif
   const int lane = lane_id();
-  const unsigned n_task = gap_stage_on(*G.matched, G.qbases) ? *G.n_task : 0u;
+  const unsigned n_task = *G.n_task;
   for (;;) {
     unsigned t = 0;
     if (lane == 0) t = atomic_add_u32(ticket, 1u);

@@ -69,10 +69,11 @@ def build_cases(scale=1):
     # DP engines: the general engine alone, and the packed engine with field spans so small that some / all reads are
     # handed over to the general engine
     cases.append(("engine_general_only", d2["contigs"], d2["reads"][:10], dict(engine=1)))
-    # stage 4a (forward extensions as tasks ahead of the walk): forced on noisy reads (the automatic rule leaves it off there),
-    # forced off on accurate reads (where the rule turns it on)
+    # stage 4a (forward extensions as tasks ahead of the walk; by rule only with >= 1000 matches per read, as in
+    # many_identical_records above): forced on noisy and on accurate reads, forced off where the rule turns it on
     cases.append(("gap_stage_forced_noisy", d2["contigs"], [rc(r) if i % 2 else r for i, r in enumerate(d2["reads"])], dict(engine=2)))
-    cases.append(("gap_stage_off_accurate", d["contigs"], mixed[:80], dict(engine=3)))
+    cases.append(("gap_stage_forced_accurate", d["contigs"], mixed[:80], dict(engine=2)))
+    cases.append(("gap_stage_off_many_records", many, [unit300, rc(unit300), unit300[10:280]] * 6, dict(engine=3)))
     cases.append(("packed_some_reads_handed_over", d2["contigs"], d2["reads"][:24], dict(pk_m_span=16)))
     cases.append(("packed_all_reads_handed_over", d2["contigs"], d2["reads"][:8], dict(pk_u_span=100)))
     return cases
