@@ -73,14 +73,17 @@ for n, name in ((1, "default_n1.json"), (2, "n2.json"), (4, "n4.json"), (8, "n8.
     eff_med = base_med / (n * med) if (s and base) else None
     bd = {k: round(v, 1) for k, v in (s.get("rank0_breakdown_ms") or {}).items() if isinstance(v, (int, float))}
     out.append("| %d | %s | %s | %s | %s / %s | %s / %s | %s |" % (n, f(d["value"], 0), f(d["e2e"]["value"], 0), f(s.get("value"), 0), f(s.get("ms_per_step"), 1), f(med, 1), f(eff, 3), f(eff_med, 3), json.dumps(bd)))
-out += ["", "Limiting terms of the sharded job at N = 8 (18.9 ms per step against 81.0 ms on one GPU): (1) the reads are 1.5 GB of ASCII on the host and the",
-        "ranks share the host's memory / PCIe bandwidth -- the rank's 187 MB are on the device after 12.7 ms (15 GB/s per rank, ~120 GB/s in aggregate;",
-        "one GPU alone gets 43 GB/s), so the upload, which one GPU hides behind 68 ms of alignment, is as long as the alignment itself (9.7 ms); (2) the index:",
-        "8.1 ms (contigs packed on rank 0 and broadcast 2.2, own 1/8 of the tables 1.3, exchange of the slices 4.4) against 11.7 ms on one GPU --",
+out += ["", "Limiting terms of the sharded job at N = 8 (18.8 ms per step against 77.5 ms on one GPU): (1) the reads are 1.5 GB of ASCII on the host and the",
+        "ranks share the host's memory / PCIe bandwidth -- the rank's 187 MB are on the device after 12.4 ms (15 GB/s per rank, ~120 GB/s in aggregate;",
+        "one GPU alone gets 43 GB/s), so the upload, which one GPU hides behind 65 ms of alignment, is longer than the alignment itself (9.3 ms of kernels); (2) the index:",
+        "7.6 ms (contigs packed on rank 0 and broadcast 2.1, own 1/8 of the tables 1.4, exchange of the slices 4.0) against 11.2 ms on one GPU --",
         "it does not shrink because the exchange (three all-gathers of 64 + 180 + 200 MB and the wait for the slowest rank) replaces the build time it saves;",
         "(3) about a millisecond of fixed cost per GPU call (launches, stream synchronisations, sort set-up) and 1 ms for gathering the rows.",
-        "Per-rank alignment itself scales: 68.8 ms / 8 = 8.6 ms against 9.7 ms measured.  `n4_strong_only_pieces*.json`: the same job at N = 4 run alone",
-        "(`--strong-only`) with 1, 2 and 4 pieces per rank: 27.4 / 26.8 / 26.8 ms.", ""]
+        "Per-rank alignment itself scales: 65.5 ms / 8 = 8.2 ms against 9.3-9.7 ms measured.  `n4_strong_only_pieces*.json` (earlier build of this round):",
+        "the same job at N = 4 run alone (`--strong-only`) with 1, 2 and 4 pieces per rank: 27.4 / 26.8 / 26.8 ms.", "",
+        "Launch list of the default command (`profiles/r02_launches.csv`, `tools/launch_list.sh`: ncu `gpu__time_duration.sum`, cold-cache and serialised,",
+        "shares only): `k_extend<0,1,0>` 97.5 % of the kernel time of a step, `k_cluster` 0.7 %, `k_seeds` 0.6 %, `k_pack` 0.6 %, the CUB radix sort 0.2 % --",
+        "the same shares as the CUDA-event stage times of the bench line (extend 115.1 of 117.3 ms = 98.1 %).", ""]
 tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
 if os.path.exists(tp):
     t = json.load(open(tp))
