@@ -4,6 +4,7 @@ Thin by design -- numpy buffers in, numpy buffers out; all computation happens i
 libmfsc_b200.so on the GPU (include/mfsc.h).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -223,6 +224,8 @@ class Engine:
             r.delta_begin = r.delta_end = r.deltas = None
             return r
         n = len(off) - 1
+        if pieces is None and os.environ.get("MFSC_ALIGN_PIECES"):
+            pieces = int(os.environ["MFSC_ALIGN_PIECES"])         # experiments
         if pieces is None:
             bases = int(off[-1] - off[0])
             pieces = min(4, bases // self.PIECE_BASES) if getattr(index, "_rate", 0.0) >= self.PIECE_MIN_RATE else 1
@@ -241,6 +244,8 @@ class Engine:
                 index._rate = float(off[-1] - off[0]) / dev_s
         return r
 
+    PIECE_WORKERS = 2             # host threads (streams) that align pieces: the tail of one piece overlaps the start of the next
+
     def _align_pipelined(self, index, buf, off, params, flags, pieces):
         import queue
         import threading
@@ -249,40 +254,59 @@ class Engine:
         targets = off[0] + (off[-1] - off[0]) * np.arange(1, pieces) // pieces
         cuts = [0] + [int(x) for x in np.searchsorted(off, targets)] + [n]
         cuts = sorted(set(cuts))
+        n_pieces = len(cuts) - 1
+        workers = max(1, min(self.PIECE_WORKERS, n_pieces))
         q = queue.Queue()
         dev = index.info()["device"]
+        parts = [None] * n_pieces
+        errors = []
 
         def up():
             E2 = None
             try:
                 E2 = Engine(self.L)
                 E2.set_device(dev)
-                for k in range(len(cuts) - 1):
+                for k in range(n_pieces):
                     lo, hi = cuts[k], cuts[k + 1]
-                    q.put(E2.upload((buf[off[lo] - off[0]:off[hi] - off[0]], off[lo:hi + 1] - off[lo])))
+                    q.put((k, E2.upload((buf[off[lo] - off[0]:off[hi] - off[0]], off[lo:hi + 1] - off[lo]))))
             except Exception as e:        # surfaced in the caller's thread
-                q.put(e)
+                errors.append(e)
             finally:
+                for _ in range(workers):
+                    q.put(None)
                 if E2 is not None:
                     E2.thread_release()
-        th = threading.Thread(target=up)
-        th.start()
-        parts = []
+
+        def work(E, own_thread):
+            try:
+                if own_thread:
+                    E.set_device(dev)
+                while True:
+                    item = q.get()
+                    if item is None:
+                        break
+                    k, rd = item
+                    try:
+                        if not errors:
+                            parts[k] = E.align_reads(index, rd, params, flags)
+                    except Exception as e:
+                        errors.append(e)
+                    finally:
+                        rd.free()
+            finally:
+                if own_thread:
+                    E.thread_release()
+
+        threads = [threading.Thread(target=up)] + [threading.Thread(target=work, args=(Engine(self.L), True)) for _ in range(workers - 1)]
+        for th in threads:
+            th.start()
         try:
-            for k in range(len(cuts) - 1):
-                rd = q.get()
-                if isinstance(rd, Exception):
-                    raise rd
-                try:
-                    parts.append(self.align_reads(index, rd, params, flags))
-                finally:
-                    rd.free()
+            work(self, False)
         finally:
-            th.join()
-            while not q.empty():
-                x = q.get()
-                if isinstance(x, Reads):
-                    x.free()
+            for th in threads:
+                th.join()
+        if errors:
+            raise errors[0]
         r = Rows()
         for f in ("ref_id", "s1", "e1", "s2", "e2", "errors", "cols"):
             setattr(r, f, np.concatenate([getattr(p, f) for p in parts]))

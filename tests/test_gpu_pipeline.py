@@ -186,3 +186,24 @@ def test_batch_over_two_gpus(gpu_engine, oracle, tmp_path):
         idx = alignerRobot.zeropadding(i)
         assert open(folder + "par" + idx + ".delta").read().split("\n")[1:] == open(folder + "serial" + idx + ".delta").read().split("\n")[1:]
     alignerRobot.set_engine(None)
+
+
+def test_pipelined_align_equals_one_call_gpu(gpu_engine):
+    """Engine.align in pieces (upload thread + two aligner threads on their own streams) returns the rows, statistics and delta
+    lists of one call."""
+    d = datagen.abun_gap(G=300_000, repeat_len=2000, L=4000, p=0.01, abun=(6, 4), seed=21)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = [r.translate(comp)[::-1] if i % 2 else r for i, r in enumerate(d["reads"])] + [b"", b"ACGT"]
+    P = engine.make_params()
+    ix = gpu_engine.index(d["contigs"], P)
+    for flags in (0, engine.WANT_DELTAS):
+        one = gpu_engine.align(ix, reads, P, flags=flags, pieces=1)
+        for k in (2, 5):
+            many = gpu_engine.align(ix, reads, P, flags=flags, pieces=k)
+            for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+                assert np.array_equal(getattr(one, f), getattr(many, f)), (f, k)
+            assert one.stats["cells"] == many.stats["cells"] and one.stats["max_band"] == many.stats["max_band"] and len(one) > 500
+            if flags:
+                for i in range(0, len(one), 7):
+                    assert np.array_equal(one.deltas[one.delta_begin[i]:one.delta_end[i]], many.deltas[many.delta_begin[i]:many.delta_end[i]])
+    ix.free()
