@@ -369,7 +369,7 @@ def measure_strong(E, args, rank, world, local, comm, torch, dist):
         ix.free()
         return wall, parts
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, args.warmup)):          # the scratch pool was trimmed before this phase: it grows back over the first steps
         one_step()
     K = max(1, min(args.steps, args.strong_steps))
     walls, last = [], None
