@@ -207,3 +207,25 @@ def test_pipelined_align_equals_one_call_gpu(gpu_engine):
                 for i in range(0, len(one), 7):
                     assert np.array_equal(one.deltas[one.delta_begin[i]:one.delta_end[i]], many.deltas[many.delta_begin[i]:many.delta_end[i]])
     ix.free()
+
+
+def test_gap_stage_on_reads_vs_reads(gpu_engine):
+    """Reads against reads at high depth (BASELINE config 4 shape: > 1000 matches per read): stage 4a switches itself on, and the
+    rows, cell counts and widest band are those of the plain walk (engine 3)."""
+    g = datagen.random_genome(150_000, np.random.default_rng(77))
+    reads, _ = datagen.noisy_reads(g, 700, 6000, 0.01, 0.01, np.random.default_rng(78))
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    dbl = []
+    for r in reads:
+        dbl += [r, r.translate(comp)[::-1]]
+    out = []
+    for eng in (0, 3):
+        P = engine.make_params(engine=eng)
+        ix = gpu_engine.index(dbl, P)
+        out.append(gpu_engine.align(ix, dbl, P))
+        ix.free()
+    a, b = out
+    assert a.stats["mems"] >= 1000 * len(dbl) and a.stats["gap_hits"] > 10_000 and b.stats["gap_hits"] == 0
+    for f in ("ref_id", "qry_id", "s1", "e1", "s2", "e2", "errors", "cols"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.stats["cells"] == b.stats["cells"] and a.stats["max_band"] == b.stats["max_band"] and a.stats["dp_calls"] == b.stats["dp_calls"]
