@@ -49,15 +49,17 @@ if d:
     r = d["roofline"]
     out += ["", "`k_extend`: %d integer operations per cell (SASS); issue view from ncu: %s" % (r["ops_per_cell"], json.dumps(r.get("issue"))), ""]
 out += ["## Workloads (BASELINE configs), N = 1, batch resident in HBM", "",
-        "| workload | Mbp/s | ms per step | seeds | sort | cluster | extend | rows back | e2e Mbp/s | DP cells | index k / HBM bytes / tables ms |", "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|"]
+        "| workload | Mbp/s | ms per step | seeds | sort | cluster | extend | rows back | e2e Mbp/s | DP cells | index k / HBM bytes / tables ms | rows == CPU oracle on the sampled reads |", "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---|"]
 for name in ("cfg1.json", "default_n1.json", "cfg3.json", "cfg4.json", "cfg4_full.json", "cfg5.json"):
     d = load(name)
     if not d:
         continue
     s = d["stage_ms_per_step"]
-    out.append("| %s | %s | %s | %s | %s | %s | %s | %s | %s | %.3g | %d / %d / %s |" % (d["config"]["workload"], f(d["value"], 0), f(d["ms_per_step"], 2), f(s["seeds"], 2), f(s["sort"], 2), f(s["cluster"], 2),
+    par = d.get("parity")
+    out.append("| %s | %s | %s | %s | %s | %s | %s | %s | %s | %.3g | %d / %d / %s | %s |" % (d["config"]["workload"], f(d["value"], 0), f(d["ms_per_step"], 2), f(s["seeds"], 2), f(s["sort"], 2), f(s["cluster"], 2),
                                                                                   f(s["extend"], 2), f(s["download"], 2), f(d["e2e"]["value"], 0), d["dp_cells_per_step"], d["config"]["index_k"],
-                                                                                  d["config"]["index_hbm_bytes"], f(d.get("index_tables_ms"), 2)))
+                                                                                  d["config"]["index_hbm_bytes"], f(d.get("index_tables_ms"), 2),
+                                                                                  ("%s: %d reads, %d rows" % ("equal" if par["equal"] else "DIFFERENT", par["reads"], par["rows"])) if par else "—"))
 out += ["", "## 1 → 8 GPUs", "",
         "| N | weak: `value` Mbp/s (cfg 2 per GPU) | weak e2e | strong: cfg 3 as one job, Mbp/s | ms per step (mean / median) | efficiency vs N = 1 (mean / median) | rank-0 breakdown of the last step (ms) |", "|---:|---:|---:|---:|---:|---:|---|"]
 base = None
