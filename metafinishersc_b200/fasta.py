@@ -6,7 +6,10 @@ size, records re-wrapped at 60 columns, parts named <base>.part-NN.fasta.  The p
 boundaries define the read batches (and therefore the row order) that
 alignerRobot.largeRvsQAlign (alignerRobot.py:258-297) concatenates.
 """
+import ctypes
 import os
+import threading
+import weakref
 
 import numpy as np
 
@@ -31,6 +34,53 @@ def read_fasta(path):
     return names, seqs
 
 
+# ------------------------------------------------------------------------------------------
+# Page-locked host buffers for what is uploaded.  A copy from pageable memory is staged by the driver at a few GB/s (measured:
+# 23 ms per 62 MB batch of parsed reads, most of it on the critical path of largeRvsQAlign); from page-locked memory the same
+# copy runs at interconnect speed.  Page-locking is slow (tens of ms per 100 MB), so blocks are pooled: a block goes back to
+# the pool when the last numpy view of it is collected, and the next parse of a similar size reuses it.
+# ------------------------------------------------------------------------------------------
+_PIN_LOCK = threading.Lock()
+_PIN_FREE = []                    # [(bytes, address)] blocks not in use
+_PIN_MIN, _PIN_MAX, _PIN_KEEP = 1 << 22, 1 << 31, 4     # below _PIN_MIN / above _PIN_MAX: pageable; blocks kept when free
+
+
+def _pin_release(L, nbytes, addr):
+    with _PIN_LOCK:
+        if len(_PIN_FREE) < _PIN_KEEP:
+            _PIN_FREE.append((nbytes, addr))
+            return
+    L.mfsc_host_free(ctypes.c_void_p(addr))
+
+
+def host_buffer(nbytes, L=None):
+    """uint8 array of nbytes for data that will be uploaded: page-locked when a device is there (pooled), else plain numpy.
+    L: the bound library (tests pass the emulation build, whose mfsc_host_alloc is malloc)."""
+    if nbytes < _PIN_MIN or nbytes > _PIN_MAX:
+        return np.empty(nbytes, dtype=np.uint8)
+    if L is None:
+        from . import _lib
+        try:
+            L = _lib.load()
+        except Exception:
+            return np.empty(nbytes, dtype=np.uint8)
+    addr = size = None
+    with _PIN_LOCK:
+        fit = [(b, a) for b, a in _PIN_FREE if nbytes <= b <= 2 * nbytes + (1 << 24)]
+        if fit:
+            size, addr = min(fit)
+            _PIN_FREE.remove((size, addr))
+    if addr is None:
+        size = (nbytes + (1 << 24) - 1) >> 24 << 24          # 16 MB granules, so that batches of similar size share blocks
+        p = ctypes.c_void_p()
+        if L.mfsc_host_alloc(ctypes.byref(p), size) != 0 or not p.value:
+            return np.empty(nbytes, dtype=np.uint8)          # no device (CPU-only run) or no page-locked memory left
+        addr = p.value
+    block = (ctypes.c_uint8 * size).from_address(addr)
+    weakref.finalize(block, _pin_release, L, size, addr).atexit = False      # at exit the process gives everything back anyway
+    return np.frombuffer(block, dtype=np.uint8, count=nbytes)
+
+
 def read_fasta_arrays(path):
     """Ingest for the aligner: -> (names list[str], uint8 bases, int64 offsets[n+1]).  Same records as read_fasta
     (blank lines skipped, sequence lines joined); one pass in C (mfsc_fasta_parse), no per-line Python work."""
@@ -42,7 +92,7 @@ def read_fasta_arrays(path):
     n_rec = ctypes.c_int32(0)
     _lib.check(L, L.mfsc_fasta_count(_lib.ptr(data), data.size, ctypes.byref(n_rec)))
     n = n_rec.value
-    bases = np.empty(max(int(data.size), 1), dtype=np.uint8)
+    bases = host_buffer(max(int(data.size), 1))
     off = np.zeros(n + 1, dtype=np.int64)
     spans = np.zeros(2 * max(n, 1), dtype=np.int64)
     _lib.check(L, L.mfsc_fasta_parse(_lib.ptr(data), data.size, _lib.ptr(bases), _lib.ptr(off), _lib.ptr(spans), n, ctypes.byref(n_rec)))

@@ -387,3 +387,33 @@ def test_pipelined_align_equals_one_call(emu_engine):
     finally:
         engine.Engine.PIECE_BASES, engine.Engine.PIECE_MIN_RATE = old
     ix.free()
+
+
+def test_host_buffer_pool(emu_engine):
+    """fasta.host_buffer: blocks come from mfsc_host_alloc (page-locked on a GPU box; malloc in the emulation build used here), stay
+    alive as long as any view of them does, and are reused by the next request of a similar size."""
+    import gc
+    from metafinishersc_b200 import fasta
+    L = emu_engine.L
+    with fasta._PIN_LOCK:
+        del fasta._PIN_FREE[:]
+    a = fasta.host_buffer(5 << 20, L)
+    assert a.size == 5 << 20 and a.flags["WRITEABLE"] and not a.flags["OWNDATA"]
+    addr = a.ctypes.data
+    a[:] = 3
+    v = a[1000:2000]
+    del a
+    gc.collect()
+    assert fasta._PIN_FREE == [] and int(v.sum()) == 3000          # a view keeps the block out of the pool
+    del v
+    gc.collect()
+    assert [b for b, _ in fasta._PIN_FREE] == [16 << 20]
+    b = fasta.host_buffer(6 << 20, L)                               # similar size: the same block again
+    assert b.ctypes.data == addr and fasta._PIN_FREE == []
+    c = fasta.host_buffer(40 << 20, L)                              # a much larger request gets its own block
+    assert c.ctypes.data != addr and c.size == 40 << 20
+    small = fasta.host_buffer(1000, L)
+    assert small.flags["OWNDATA"]                                   # small buffers stay pageable
+    del b, c
+    gc.collect()
+    assert len(fasta._PIN_FREE) == 2
