@@ -1628,17 +1628,49 @@ int mfsc_write_delta(const char* path, const char* ref_path, const char* qry_pat
 // ------------------------------------------------------------------------------------------
 // FASTA ingest / part writing (host)
 // ------------------------------------------------------------------------------------------
+// header lines of data[b, e), b at the start of a line
+static int64_t fasta_count_lines(const uint8_t* data, int64_t b, int64_t e) {
+  int64_t c = 0, i = b;
+  while (i < e) {
+    if (data[i] == '>') c++;
+    const void* nl = memchr(data + i, '\n', (size_t)(e - i));
+    if (!nl) break;
+    i = (const uint8_t*)nl - data + 1;
+  }
+  return c;
+}
+
+static int fasta_threads(int64_t n) {
+  if (n <= (int64_t)(8 << 20)) return 1;
+  return (int)std::min<int64_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+}
+
 int mfsc_fasta_count(const uint8_t* data, int64_t n, int32_t* n_rec_out) {
   if (!data || n < 0 || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_count: bad arguments");
-  int32_t c = 0;
-  int64_t i = 0;
-  while (i < n) {
-    if (data[i] == '>') c++;
-    const void* e = memchr(data + i, '\n', (size_t)(n - i));
-    if (!e) break;
-    i = (const uint8_t*)e - data + 1;
+  // chunks that begin at the start of a line, counted by a few host threads
+  const int T = fasta_threads(n);
+  std::vector<int64_t> cb(1, 0);
+  for (int t = 1; t < T; t++) {
+    int64_t p = n * t / T;
+    if (p <= cb.back()) continue;
+    const void* nl = memchr(data + p, '\n', (size_t)(n - p));
+    if (!nl) break;
+    p = (const uint8_t*)nl - data + 1;
+    if (p < n && p > cb.back()) cb.push_back(p);
   }
-  *n_rec_out = c;
+  cb.push_back(n);
+  const int C = (int)cb.size() - 1;
+  std::vector<int64_t> cnt(C, 0);
+  {
+    std::vector<std::thread> th;
+    for (int c = 1; c < C; c++) th.emplace_back([&, c]() { cnt[c] = fasta_count_lines(data, cb[c], cb[c + 1]); });
+    cnt[0] = fasta_count_lines(data, cb[0], cb[1]);
+    for (auto& x : th) x.join();
+  }
+  int64_t total = 0;
+  for (int c = 0; c < C; c++) total += cnt[c];
+  if (total > 0x7fffffff) return fail(MFSC_ERR_ARG, "mfsc_fasta_count: more than 2^31 records");
+  *n_rec_out = (int32_t)total;
   return MFSC_OK;
 }
 
@@ -1673,8 +1705,7 @@ int mfsc_fasta_parse(const uint8_t* data, int64_t n, uint8_t* bases_out, int64_t
                      int32_t* n_rec_out) {
   if (!data || n < 0 || !bases_out || !off_out || !name_span_out || !n_rec_out) return fail(MFSC_ERR_ARG, "mfsc_fasta_parse: bad arguments");
   // chunks that begin at header lines, parsed by a few host threads: count, prefix sums, copy
-  int T = 1;
-  if (n > (int64_t)(8 << 20)) { T = (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())); }
+  const int T = fasta_threads(n);
   std::vector<int64_t> cb(1, 0);
   for (int t = 1; t < T; t++) {
     int64_t p = n * t / T;

@@ -417,3 +417,31 @@ def test_host_buffer_pool(emu_engine):
     del b, c
     gc.collect()
     assert len(fasta._PIN_FREE) == 2
+
+
+def test_fasta_arrays_threaded_paths(tmp_path):
+    """mfsc_fasta_count / mfsc_fasta_parse above 8 MB run on several host threads (chunks cut at line starts / header lines): same
+    names and sequences as the line-by-line Python reader on a file with wrapped, unwrapped, CRLF and blank lines."""
+    from metafinishersc_b200 import fasta
+    rng = np.random.default_rng(3)
+    recs, p = [], str(tmp_path / "x.fasta")
+    with open(p, "wb") as f:
+        f.write(b"ACGT stray line before any header\n")
+        for i in range(2500):
+            L = int(rng.integers(1, 9000))
+            s = bytes(rng.choice(list(b"ACGTN"), size=L).astype(np.uint8))
+            w = int(rng.choice([0, 60, 70, 1]))
+            f.write(b">r%d some text\r\n" % i if i % 5 == 0 else b">r%d\n" % i)
+            if w == 0:
+                f.write(s + b"\n")
+            else:
+                for k in range(0, L, w):
+                    f.write(s[k:k + w] + (b"\r\n" if i % 7 == 0 else b"\n"))
+            if i % 11 == 0:
+                f.write(b"\n\n")
+            recs.append(s)
+    assert os.path.getsize(p) > (8 << 20)
+    names, bases, off = fasta.read_fasta_arrays(p)
+    n2, s2 = fasta.read_fasta(p)
+    assert names == n2 and len(names) == 2500
+    assert all(bases[off[i]:off[i + 1]].tobytes() == recs[i] == s2[i] for i in range(2500))
