@@ -323,8 +323,11 @@ def _align_job(folderName, outputName, referenceName, queryName, specialForRaw, 
     return rs
 
 
-_SUPER_BASES = 64_000_000      # query bases per GPU call when jobs are merged (a 10 kb noisy read keeps one warp busy for
-                               # milliseconds, so a 12.5 Mbp part alone fills a quarter of the resident warps)
+_SUPER_BASES = 256_000_000     # query bases per GPU call when jobs are merged.  A 10 kb noisy read keeps one warp busy for
+                               # milliseconds, so a 12.5 Mbp part alone fills a quarter of the resident warps, and every call ends
+                               # on the tail of its slowest reads: measured on cfg 2 (250 Mbp in 20 parts, tools/super_batch_sweep.py)
+                               # 32 Mbp per call 247 ms, 64: 189, 96: 186, 128: 204, one call: 178 ms -- the tails cost more than
+                               # overlapping the upload of the next call saves.  Larger inputs still go in several calls.
 
 
 def _merge_queries(entries):

@@ -445,3 +445,25 @@ def test_fasta_arrays_threaded_paths(tmp_path):
     n2, s2 = fasta.read_fasta(p)
     assert names == n2 and len(names) == 2500
     assert all(bases[off[i]:off[i + 1]].tobytes() == recs[i] == s2[i] for i in range(2500))
+
+
+def test_merged_calls_of_any_size_write_the_same_files(emu_engine, tmp_path):
+    """The 20 jobs of largeRvsQAlign are merged into GPU calls of up to alignerRobot._SUPER_BASES query bases (uploads of the next
+    call on a second thread): the rows and every per-part file are the same whether that is one call, a few, or one per part."""
+    alignerRobot.set_engine(emu_engine)
+    folder, d, reads = make_folder(tmp_path, n_reads=120)
+    old = alignerRobot._SUPER_BASES
+    outs = {}
+    try:
+        for tag, sb in (("one", 1 << 40), ("few", 60_000), ("each", 1)):
+            alignerRobot._SUPER_BASES = sb
+            outs[tag] = alignerRobot.largeRvsQAlign(folder, 20, "", "LC_filtered", "SR", tag)
+    finally:
+        alignerRobot._SUPER_BASES = old
+        alignerRobot.set_engine(None)
+    assert outs["one"] == outs["few"] == outs["each"] and len(outs["one"]) > 100
+    for i in range(1, 21):
+        idx = alignerRobot.zeropadding(i)
+        for tag in ("few", "each"):
+            assert open(folder + tag + idx + "Out").read().split("\n")[1:] == open(folder + "one" + idx + "Out").read().split("\n")[1:]
+            assert open(folder + tag + idx + ".delta").read().split("\n")[1:] == open(folder + "one" + idx + ".delta").read().split("\n")[1:]
